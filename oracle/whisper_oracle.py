@@ -50,7 +50,7 @@ class Oracle:
     """fp32 restatement. `weights` is {state_dict name: ndarray/tensor}; `cfg` the reference's _config.json dict."""
 
     def __init__(self, weights, cfg):
-        self.W = {k: torch.as_tensor(np.asarray(v)).float() for k, v in weights.items()}
+        self.W = {k: torch.from_numpy(np.array(v, dtype=np.float32)) for k, v in weights.items()}
         self.cfg = cfg
         self.d = int(cfg["n_text_state"])
         self.n_head_audio = int(cfg["n_audio_head"])

@@ -1,0 +1,111 @@
+"""Shared test helpers: seeded synthetic audio, model directories, oracle access, comparison rules."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (os.path.join(ROOT, "tools"), os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import make_model  # noqa: E402
+
+MODEL_CACHE = os.environ.get("B200W_MODEL_CACHE", "/tmp/b200w_models")
+MEL_TOL = 1e-4          # north_star: mel within 1e-4 absolute
+LOGIT_TOL = 0.05        # bf16 tolerance on logits (abs); token mismatches are accepted only under this top-2 margin
+ENC_REL_TOL = 2e-2      # max-abs error of cross K/V relative to max-abs of the reference tensor
+ENC_COS_TOL = 0.999
+
+
+def synth_audio(dist, n, seed):
+    """N = 0.1*N(0,1) clipped, U = U(-1,1), S = 5 AM sines 80-4000 Hz + 0.01*N(0,1)."""
+    rng = np.random.default_rng(seed)
+    if dist == "N":
+        return np.clip(0.1 * rng.standard_normal(n), -1, 1).astype(np.float32)
+    if dist == "U":
+        return rng.uniform(-1, 1, n).astype(np.float32)
+    if dist == "S":
+        t = np.arange(n) / 16000.0
+        x = np.zeros(n)
+        for _ in range(5):
+            f = rng.uniform(80, 4000)
+            am = rng.uniform(2, 8)
+            x += rng.uniform(0.05, 0.2) * np.sin(2 * np.pi * f * t + rng.uniform(0, 6.28)) * (0.6 + 0.4 * np.sin(2 * np.pi * am * t))
+        x += 0.01 * rng.standard_normal(n)
+        return np.clip(x, -1, 1).astype(np.float32)
+    if dist == "T":  # adversarial: pure tones, no noise floor
+        t = np.arange(n) / 16000.0
+        return (0.5 * np.sin(2 * np.pi * 440.0 * t) + 0.3 * np.sin(2 * np.pi * 1234.5 * t)).astype(np.float32)
+    raise ValueError(dist)
+
+
+def model_root(arch):
+    """Builds (once per box) the seeded random-init model directory for `arch`; returns the model root."""
+    d = os.path.join(MODEL_CACHE, arch)
+    marker = os.path.join(d, ".complete")
+    if not os.path.exists(marker):
+        make_model.build_model_dir(MODEL_CACHE, arch)
+        open(marker, "w").write("ok")
+    return MODEL_CACHE
+
+
+_oracles = {}
+
+
+def load_oracle(arch):
+    import whisper_oracle
+
+    if arch not in _oracles:
+        W, cfg = make_model.load_model_dir(model_root(arch), arch)
+        _oracles[arch] = whisper_oracle.Oracle(W, cfg)
+    return _oracles[arch]
+
+
+_melref = None
+
+
+def mel_ref_lib():
+    """oracle/_ref/libmel_ref.so (the reference's own frontend) or None if it was not built."""
+    global _melref
+    if _melref is None:
+        path = os.path.join(ROOT, "oracle", "_ref", "libmel_ref.so")
+        _melref = ctypes.CDLL(path) if os.path.exists(path) else False
+    return _melref or None
+
+
+def reference_mel(audios, n_mels):
+    """[B, n_mels, 3000] from the reference frontend when built, else from the numpy restatement."""
+    lib = mel_ref_lib()
+    out = np.zeros((len(audios), n_mels, 3000), np.float32)
+    if lib is not None:
+        for i, a in enumerate(audios):
+            a = np.ascontiguousarray(a, np.float32)
+            rc = lib.melref_preprocess(a.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), len(a), n_mels,
+                                       out[i].ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
+            assert rc > 0
+        return out
+    import mel_oracle
+
+    for i, a in enumerate(audios):
+        out[i] = mel_oracle.log_mel(a, n_mels)
+    return out
+
+
+def tokens_agree(got, exp, margins, tol):
+    """Greedy sequences must be identical up to the first step whose reference top-2 margin is below `tol`
+    (after such a step the free-running sequences may legitimately diverge)."""
+    for b in range(len(exp)):
+        for i in range(min(len(got[b]), len(exp[b]))):
+            if got[b][i] != exp[b][i]:
+                if margins[i][b] >= tol:
+                    return False
+                break
+    return True
+
+
+def cosine(a, b):
+    a = a.ravel().astype(np.float64)
+    b = b.ravel().astype(np.float64)
+    return float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-30))

@@ -1,0 +1,158 @@
+// libax_whisper.so outer boundary: the reference's four AX_WHISPER_* entry points
+// (/root/reference/cpp/src/api/ax_whisper_api.cpp:48-163) over the B200 engine, plus batched extensions.
+// Also holds the small host pieces the reference takes from third-party headers: a WAV reader (the reference uses
+// AudioFile.h, GPLv3 -- re-written, not copied), the token table loader (Whisper.cpp:115-127) and a length-safe
+// base64 decoder (the reference's writes into char[32], Whisper.cpp:226-228).
+#include "../../include/ax_whisper_api.h"
+
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "engine.h"
+#include "host_utils.h"
+
+using namespace b200w;
+
+namespace {
+
+thread_local std::string g_api_err;
+
+struct WhisperHandle {
+  std::unique_ptr<Engine> engine;
+  std::vector<std::string> token_table;  // base64 text per id (line index = id, Whisper.cpp:123-126)
+  std::string lang;
+  std::mutex mu;
+};
+
+void set_err(const std::string& s) {
+  g_api_err = s;
+  fprintf(stderr, "[ax_whisper] %s\n", s.c_str());
+}
+
+std::string detokenize(const WhisperHandle& h, const std::vector<int>& ids) {
+  std::string s;
+  for (int id : ids) {
+    if (id < 0 || (size_t)id >= h.token_table.size()) continue;  // specials (>= 50257) carry no text; the reference indexes OOB here
+    s += base64_decode(h.token_table[id]);
+  }
+  // The reference converts Traditional -> Simplified Chinese with OpenCC when lang == "zh" (Whisper.cpp:231-236); its
+  // prebuilt OpenCC is AArch64-only and the conversion is text cosmetics, not arithmetic: identity here.
+  return s;
+}
+
+int run_batch(WhisperHandle* h, const float* const* pcm, const int* n_samples, int B, const DecodeOptions& opt,
+              std::vector<std::vector<int>>* toks) {
+  try {
+    std::lock_guard<std::mutex> lock(h->mu);
+    h->engine->transcribe(pcm, n_samples, B, h->lang, opt, toks, nullptr);
+    return 0;
+  } catch (const std::exception& ex) {
+    set_err(std::string("run whisper failed: ") + ex.what());
+    return -1;
+  } catch (...) {
+    set_err("run whisper failed: unknown error");
+    return -1;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+AX_WHISPER_API const char* AX_WHISPER_LastError(void) { return g_api_err.c_str(); }
+
+AX_WHISPER_API AX_WHISPER_HANDLE AX_WHISPER_Init(const char* model_type, const char* model_path, const char* language) {
+  if (!model_type || !model_path || !language) return nullptr;
+  try {
+    g_api_err.clear();
+    std::unique_ptr<WhisperHandle> h(new WhisperHandle());
+    const char* dev_env = getenv("B200W_DEVICE");
+    const char* mb_env = getenv("B200W_MAX_BATCH");
+    h->engine.reset(new Engine(model_path, model_type, dev_env ? atoi(dev_env) : 0, mb_env ? atoi(mb_env) : 1));
+    const std::string token_path = std::string(model_path) + "/" + model_type + "/" + model_type + "-tokens.txt";
+    std::ifstream fs(token_path);
+    if (!fs.is_open()) {
+      set_err("Can NOT open " + token_path);
+      return nullptr;
+    }
+    std::string line;
+    while (std::getline(fs, line)) h->token_table.push_back(line.substr(0, line.find(' ')));
+    h->engine->sot_sequence(language, &h->lang);  // resolves the "unknown language -> zh" fallback once
+    return static_cast<AX_WHISPER_HANDLE>(h.release());
+  } catch (const std::exception& ex) {
+    set_err(std::string("load models failed: ") + ex.what());
+    return nullptr;  // unlike the reference (ax_whisper_api.cpp:49-53) nothing is leaked on failure
+  } catch (...) {
+    set_err("load models failed: unknown error");
+    return nullptr;
+  }
+}
+
+AX_WHISPER_API void AX_WHISPER_Uninit(AX_WHISPER_HANDLE handle) {
+  if (handle) delete static_cast<WhisperHandle*>(handle);
+}
+
+AX_WHISPER_API int AX_WHISPER_RunPCM(AX_WHISPER_HANDLE handle, float* pcm_data, int num_samples, char** result) {
+  if (!handle || !pcm_data || !result) return -1;
+  *result = nullptr;
+  WhisperHandle* h = static_cast<WhisperHandle*>(handle);
+  const float* ptrs[1] = {pcm_data};
+  std::vector<std::vector<int>> toks;
+  if (run_batch(h, ptrs, &num_samples, 1, DecodeOptions(), &toks) != 0) return -1;
+  *result = strdup(detokenize(*h, toks[0]).c_str());
+  return *result ? 0 : -1;
+}
+
+AX_WHISPER_API int AX_WHISPER_RunFile(AX_WHISPER_HANDLE handle, const char* wav_file, char** result) {
+  if (!handle || !wav_file || !result) return -1;
+  *result = nullptr;
+  WavData wav;
+  std::string err;
+  if (!load_wav(wav_file, &wav, &err)) {
+    set_err("load wav failed: " + err);
+    return -1;
+  }
+  if (wav.sample_rate != 16000)
+    fprintf(stderr, "[ax_whisper] warning: %s is %d Hz; it is treated as 16 kHz like the reference does\n", wav_file, wav.sample_rate);
+  // mono mix only for stereo; with more channels the first one is used (ax_whisper_api.cpp:105-113)
+  std::vector<float>& s = wav.channels[0];
+  if (wav.channels.size() == 2)
+    for (size_t i = 0; i < s.size(); ++i) s[i] = (s[i] + wav.channels[1][i]) / 2;
+  return AX_WHISPER_RunPCM(handle, s.data(), (int)s.size(), result);
+}
+
+AX_WHISPER_API int AX_WHISPER_RunPCMBatch(AX_WHISPER_HANDLE handle, const float* const* pcm_data, const int* num_samples, int batch,
+                                          char** results) {
+  if (!handle || !pcm_data || !num_samples || !results || batch <= 0) return -1;
+  for (int i = 0; i < batch; ++i) results[i] = nullptr;
+  WhisperHandle* h = static_cast<WhisperHandle*>(handle);
+  std::vector<std::vector<int>> toks;
+  if (run_batch(h, pcm_data, num_samples, batch, DecodeOptions(), &toks) != 0) return -1;
+  for (int i = 0; i < batch; ++i) results[i] = strdup(detokenize(*h, toks[i]).c_str());
+  return 0;
+}
+
+AX_WHISPER_API int AX_WHISPER_RunPCMTokens(AX_WHISPER_HANDLE handle, const float* const* pcm_data, const int* num_samples, int batch,
+                                           int max_new_tokens, int honor_eot, int* tokens, int max_tokens, int* n_tokens) {
+  if (!handle || !pcm_data || !num_samples || !tokens || !n_tokens || batch <= 0 || max_tokens <= 0) return -1;
+  WhisperHandle* h = static_cast<WhisperHandle*>(handle);
+  DecodeOptions opt;
+  if (max_new_tokens > 0) opt.max_new_tokens = std::min(max_new_tokens, kTextCtx - kSotLen);
+  opt.honor_eot = honor_eot != 0;
+  std::vector<std::vector<int>> toks;
+  if (run_batch(h, pcm_data, num_samples, batch, opt, &toks) != 0) return -1;
+  for (int b = 0; b < batch; ++b) {
+    const int n = std::min<int>((int)toks[b].size(), max_tokens);
+    for (int i = 0; i < n; ++i) tokens[(size_t)b * max_tokens + i] = toks[b][i];
+    n_tokens[b] = n;
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,332 @@
+// K7: the HBM-bound kernels of one greedy decoder step (everything of the step that is not a GEMM).
+//
+// One step = TextDecoderTensorCache.forward of the reference (/root/reference/model_convert/export_onnx.py:312-387)
+// plus the host glue of Whisper::run_decoder (/root/reference/cpp/src/Whisper.cpp:290-346), for B sequences at once:
+//   embed            token_embedding[token] + positional_embedding[offset]              export_onnx.py:334-336
+//   self attention   static 448-slot cache + current token, mask == "positions < offset"  :103-147 (mask value -60000
+//                    underflows to exactly 0 in the fp32 softmax, so attending to positions 0..offset is identical);
+//                    the row append the reference does on the host (Whisper.cpp:328-342) happens in the kernel
+//   cross attention  1500 encoder keys, no mask                                           :216-230
+//   argmax           first maximum (std::max_element, Whisper.cpp:42-45), EOT / loop bookkeeping (:214-222)
+// K/V live in HBM as bf16, head-major [B][H][n][64]: one (sequence, head) is a contiguous 128-byte-per-key stream,
+// read with 16-byte loads (8 lanes per key, 4 keys per warp instruction), fp32 scores / softmax / accumulation.
+#include <cfloat>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b200w {
+namespace {
+
+__device__ __forceinline__ uint4 ld_stream16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float dot8(const uint4& kv, const float (&q)[8]) {
+  float a = bf16lo_to_f32(kv.x) * q[0];
+  a = fmaf(bf16hi_to_f32(kv.x), q[1], a);
+  a = fmaf(bf16lo_to_f32(kv.y), q[2], a);
+  a = fmaf(bf16hi_to_f32(kv.y), q[3], a);
+  a = fmaf(bf16lo_to_f32(kv.z), q[4], a);
+  a = fmaf(bf16hi_to_f32(kv.z), q[5], a);
+  a = fmaf(bf16lo_to_f32(kv.w), q[6], a);
+  a = fmaf(bf16hi_to_f32(kv.w), q[7], a);
+  return a;
+}
+__device__ __forceinline__ void axpy8(float (&acc)[8], float p, const uint4& v) {
+  acc[0] = fmaf(p, bf16lo_to_f32(v.x), acc[0]);
+  acc[1] = fmaf(p, bf16hi_to_f32(v.x), acc[1]);
+  acc[2] = fmaf(p, bf16lo_to_f32(v.y), acc[2]);
+  acc[3] = fmaf(p, bf16hi_to_f32(v.y), acc[3]);
+  acc[4] = fmaf(p, bf16lo_to_f32(v.z), acc[4]);
+  acc[5] = fmaf(p, bf16hi_to_f32(v.z), acc[5]);
+  acc[6] = fmaf(p, bf16lo_to_f32(v.w), acc[6]);
+  acc[7] = fmaf(p, bf16hi_to_f32(v.w), acc[7]);
+}
+
+constexpr float kScoreScaleLog2 = 0.125f * 1.4426950408889634f;  // (64^-0.25)^2 * log2(e)
+
+// Attention of ONE query over keys [k_begin, k_end) of a contiguous bf16 [n][64] K and V stream.
+// All NT threads of the CTA participate.  Scores are kept in smem (log2 domain).  Optional extra "current token"
+// (fp32 k1/v1, used by self attention).  Returns through smem: s_out[64] = unnormalised sum_j p_j v_j,
+// *s_m = running max (log2 domain), *s_l = sum_j p_j.
+template <int NT>
+__device__ __forceinline__ void attend_one_query(const float* __restrict__ q_global /*[64] f32*/, const __nv_bfloat16* __restrict__ K,
+                                                 const __nv_bfloat16* __restrict__ V, int k_begin, int k_end, const float* k1,
+                                                 const float* v1, float* s_scores, float* s_red, float* s_out, float* s_ml) {
+  constexpr int NW = NT / 32;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grp = lane >> 3, sub = lane & 7;  // 4 keys per warp instruction, 8 lanes (16 B each) per key
+  float q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) q[i] = q_global[sub * 8 + i] * kScoreScaleLog2;
+  const int n = k_end - k_begin;
+
+  // ---- phase 1: scores ----
+  float mx = -INFINITY;
+  constexpr int U = 4;  // independent 16-byte loads in flight per thread
+  for (int jb = warp * 4; jb < n; jb += NW * 4 * U) {  // warp-uniform bounds: the shuffles below need every lane
+    const int j0 = jb + grp;
+    uint4 kv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int j = j0 + u * NW * 4;
+      kv[u] = j < n ? ld_stream16(K + (long)(k_begin + j) * 64 + sub * 8) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int j = j0 + u * NW * 4;
+      float s = dot8(kv[u], q);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      if (j < n) {
+        if (sub == 0) s_scores[j] = s;
+        mx = fmaxf(mx, s);
+      }
+    }
+  }
+  float s_cur = -INFINITY;
+  if (k1 != nullptr) {  // current token: fp32 k1 (every thread computes it redundantly: 64 MACs)
+    float a = 0.f;
+#pragma unroll 8
+    for (int i = 0; i < 64; ++i) a = fmaf(q_global[i] * kScoreScaleLog2, k1[i], a);
+    s_cur = a;
+    mx = fmaxf(mx, s_cur);
+  }
+  mx = warp_max(mx);
+  if (lane == 0) s_red[warp] = mx;
+  __syncthreads();
+  float m = s_red[0];
+#pragma unroll
+  for (int w = 1; w < NW; ++w) m = fmaxf(m, s_red[w]);
+  __syncthreads();
+
+  // ---- phase 2: softmax weights and P.V ----
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  float lsum = 0.f;
+  for (int jb = warp * 4; jb < n; jb += NW * 4 * U) {
+    const int j0 = jb + grp;
+    uint4 vv[U];
+    float p[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int j = j0 + u * NW * 4;
+      const bool ok = j < n;
+      vv[u] = ok ? ld_stream16(V + (long)(k_begin + j) * 64 + sub * 8) : make_uint4(0, 0, 0, 0);
+      p[u] = ok ? exp2f(s_scores[j] - m) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      axpy8(acc, p[u], vv[u]);
+      if (sub == 0) lsum += p[u];
+    }
+  }
+  // reduce the 4 key groups of the warp, then the warps
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
+    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+  }
+  lsum = warp_sum(lsum);
+  float* s_acc = s_scores;  // scores are dead now; reuse as [NW][64] (+ NW sums)
+  __syncthreads();
+  if (grp == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_acc[warp * 64 + sub * 8 + i] = acc[i];
+  }
+  if (lane == 0) s_red[warp] = lsum;
+  __syncthreads();
+  if (tid < 64) {
+    float o = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) o += s_acc[w * 64 + tid];
+    float l = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) l += s_red[w];
+    if (k1 != nullptr) {
+      const float pc = exp2f(s_cur - m);
+      o = fmaf(pc, v1[tid], o);
+      l += pc;
+    }
+    s_out[tid] = o;
+    if (tid == 0) {
+      s_ml[0] = m;
+      s_ml[1] = l;
+    }
+  }
+  __syncthreads();
+}
+
+// ---- embedding -------------------------------------------------------------------------------------------
+__global__ void embed_kernel(const int* __restrict__ step_ptr, const int* __restrict__ tokens, const float* __restrict__ tok_emb,
+                             const float* __restrict__ pos_emb, float* __restrict__ x, int d, int n_text_ctx) {
+  const int b = blockIdx.x;
+  const int step = *step_ptr;
+  const int tok = tokens[(long)b * n_text_ctx + step];
+  const float4* te = reinterpret_cast<const float4*>(tok_emb + (long)tok * d);
+  const float4* pe = reinterpret_cast<const float4*>(pos_emb + (long)step * d);
+  float4* xo = reinterpret_cast<float4*>(x + (long)b * d);
+  for (int i = threadIdx.x; i < d / 4; i += blockDim.x) {
+    const float4 a = te[i], p = pe[i];
+    xo[i] = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
+  }
+}
+
+// ---- self attention ----------------------------------------------------------------------------------------
+constexpr int kSelfThreads = 128;
+__global__ void __launch_bounds__(kSelfThreads) self_attention_decode_kernel(const float* __restrict__ qkv, __nv_bfloat16* __restrict__ k_cache,
+                                                                            __nv_bfloat16* __restrict__ v_cache, const int* __restrict__ step_ptr,
+                                                                            __nv_bfloat16* __restrict__ out, int n_head, int n_ctx) {
+  __shared__ float s_scores[512];
+  __shared__ float s_red[kSelfThreads / 32];
+  __shared__ float s_out[64];
+  __shared__ float s_ml[2];
+  __shared__ float s_k1[64], s_v1[64];
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int d = n_head * 64;
+  const int pos = *step_ptr;  // cached positions 0..pos-1, current token at pos
+  const float* q = qkv + (long)b * 3 * d + h * 64;
+  const float* k1 = q + d;
+  const float* v1 = q + 2 * d;
+  __nv_bfloat16* Kc = k_cache + ((long)b * n_head + h) * n_ctx * 64;
+  __nv_bfloat16* Vc = v_cache + ((long)b * n_head + h) * n_ctx * 64;
+  if (threadIdx.x < 64) {
+    s_k1[threadIdx.x] = k1[threadIdx.x];
+    s_v1[threadIdx.x] = v1[threadIdx.x];
+  }
+  __syncthreads();
+  attend_one_query<kSelfThreads>(q, Kc, Vc, 0, pos, s_k1, s_v1, s_scores, s_red, s_out, s_ml);
+  if (threadIdx.x < 64) {
+    out[(long)b * d + h * 64 + threadIdx.x] = __float2bfloat16_rn(s_out[threadIdx.x] / s_ml[1]);
+    // append this token's key / value (the reference does this on the host after the step, Whisper.cpp:328-342)
+    Kc[(long)pos * 64 + threadIdx.x] = __float2bfloat16_rn(s_k1[threadIdx.x]);
+    Vc[(long)pos * 64 + threadIdx.x] = __float2bfloat16_rn(s_v1[threadIdx.x]);
+  }
+}
+
+// ---- cross attention ---------------------------------------------------------------------------------------
+constexpr int kCrossThreads = 256;
+__global__ void __launch_bounds__(kCrossThreads) cross_attention_decode_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ k,
+                                                                              const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ out,
+                                                                              int n_head, int T, int n_split, float* __restrict__ part_m,
+                                                                              float* __restrict__ part_l, float* __restrict__ part_o) {
+  __shared__ float s_scores[kCrossThreads / 32 * 64 > 1504 ? kCrossThreads / 32 * 64 : 1504];
+  __shared__ float s_red[kCrossThreads / 32];
+  __shared__ float s_out[64];
+  __shared__ float s_ml[2];
+  const int h = blockIdx.x / n_split, sp = blockIdx.x % n_split;
+  const int b = blockIdx.y;
+  const int d = n_head * 64;
+  const long kv_off = ((long)b * n_head + h) * T * 64;
+  const int per = (T + n_split - 1) / n_split;
+  const int k_begin = sp * per, k_end = min(T, k_begin + per);
+  attend_one_query<kCrossThreads>(q + (long)b * d + h * 64, k + kv_off, v + kv_off, k_begin, k_end, nullptr, nullptr, s_scores, s_red,
+                                  s_out, s_ml);
+  if (n_split == 1) {
+    if (threadIdx.x < 64) out[(long)b * d + h * 64 + threadIdx.x] = __float2bfloat16_rn(s_out[threadIdx.x] / s_ml[1]);
+  } else {
+    const long pi = ((long)b * n_head + h) * n_split + sp;
+    if (threadIdx.x < 64) part_o[pi * 64 + threadIdx.x] = s_out[threadIdx.x];
+    if (threadIdx.x == 0) {
+      part_m[pi] = s_ml[0];
+      part_l[pi] = s_ml[1];
+    }
+  }
+}
+
+__global__ void cross_attention_combine_kernel(const float* __restrict__ part_m, const float* __restrict__ part_l,
+                                               const float* __restrict__ part_o, __nv_bfloat16* __restrict__ out, int n_head, int n_split) {
+  const int h = blockIdx.x, b = blockIdx.y, t = threadIdx.x;  // 64 threads
+  const long base = ((long)b * n_head + h) * n_split;
+  float m = -INFINITY;
+  for (int s = 0; s < n_split; ++s) m = fmaxf(m, part_m[base + s]);
+  float o = 0.f, l = 0.f;
+  for (int s = 0; s < n_split; ++s) {
+    const float w = exp2f(part_m[base + s] - m);
+    o = fmaf(w, part_o[(base + s) * 64 + t], o);
+    l = fmaf(w, part_l[base + s], l);
+  }
+  out[((long)b * n_head + h) * 64 + t] = __float2bfloat16_rn(o / l);
+}
+
+// ---- argmax finalize + loop bookkeeping --------------------------------------------------------------------
+__global__ void __launch_bounds__(128) argmax_finalize_kernel(DecodeState st, const float* __restrict__ part_val, const int* __restrict__ part_idx,
+                                                              int n_tiles, int part_ld, int n_text_ctx, int eot, int honor_eot, int sot_len) {
+  __shared__ float s_v[4];
+  __shared__ int s_i[4];
+  const int b = blockIdx.x;
+  float best = -FLT_MAX;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < n_tiles; i += blockDim.x) {
+    const float v = part_val[(long)b * part_ld + i];
+    const int ix = part_idx[(long)b * part_ld + i];
+    if (v > best || (v == best && ix < bi)) best = v, bi = ix;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) best = ov, bi = oi;
+  }
+  if ((threadIdx.x & 31) == 0) s_v[threadIdx.x >> 5] = best, s_i[threadIdx.x >> 5] = bi;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 4; ++w)
+      if (s_v[w] > best || (s_v[w] == best && s_i[w] < bi)) best = s_v[w], bi = s_i[w];
+    const int pos = *st.step;
+    st.out_tokens[(long)b * n_text_ctx + pos] = bi;
+    if (pos + 1 >= sot_len && pos + 1 < n_text_ctx) {
+      const int f = st.forced ? st.forced[(long)b * n_text_ctx + pos + 1] : -1;
+      st.tokens[(long)b * n_text_ctx + pos + 1] = f >= 0 ? f : bi;
+    }
+    if (honor_eot && pos >= sot_len - 1 && bi == eot) st.finished[b] = 1;
+  }
+}
+
+__global__ void advance_step_kernel(int* step) { *step += 1; }
+
+}  // namespace
+
+void launch_embed(const DecodeState& st, const float* tok_emb, const float* pos_emb, float* x, int B, int d, int n_text_ctx,
+                  cudaStream_t stream) {
+  embed_kernel<<<B, 128, 0, stream>>>(st.step, st.tokens, tok_emb, pos_emb, x, d, n_text_ctx);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_self_attention_decode(const float* qkv, __nv_bfloat16* k_cache, __nv_bfloat16* v_cache, const int* step, __nv_bfloat16* out,
+                                  int B, int n_head, int n_ctx, cudaStream_t stream) {
+  dim3 grid(n_head, B);
+  self_attention_decode_kernel<<<grid, kSelfThreads, 0, stream>>>(qkv, k_cache, v_cache, step, out, n_head, n_ctx);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+int cross_attention_pick_split(int B, int n_head) {
+  // enough CTAs for ~4 per SM; a single split once the batch provides them
+  int split = 1;
+  while (B * n_head * split < 4 * kNumSMs && split < 8) split *= 2;
+  return split;
+}
+
+void launch_cross_attention_decode(const float* q, const __nv_bfloat16* k, const __nv_bfloat16* v, __nv_bfloat16* out, int B, int n_head,
+                                   int T, int n_split, float* part_m, float* part_l, float* part_o, cudaStream_t stream) {
+  dim3 grid(n_head * n_split, B);
+  cross_attention_decode_kernel<<<grid, kCrossThreads, 0, stream>>>(q, k, v, out, n_head, T, n_split, part_m, part_l, part_o);
+  if (n_split > 1) {
+    dim3 g2(n_head, B);
+    cross_attention_combine_kernel<<<g2, 64, 0, stream>>>(part_m, part_l, part_o, out, n_head, n_split);
+  }
+  CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_argmax_finalize(const DecodeState& st, const float* part_val, const int* part_idx, int n_tiles, int part_ld, int B,
+                            int n_text_ctx, int eot, int honor_eot, int sot_len, cudaStream_t stream) {
+  argmax_finalize_kernel<<<B, 128, 0, stream>>>(st, part_val, part_idx, n_tiles, part_ld, n_text_ctx, eot, honor_eot, sot_len);
+  advance_step_kernel<<<1, 1, 0, stream>>>(st.step);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace b200w

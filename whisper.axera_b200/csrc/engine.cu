@@ -1,0 +1,740 @@
+// Engine implementation: model loading, HBM layout, stage orchestration, CUDA-graphed greedy loop.
+// Reference anchors: Whisper::load_models (/root/reference/cpp/src/Whisper.cpp:86-149), Whisper::run (:186-239),
+// Whisper::run_decoder (:290-346); graph semantics from /root/reference/model_convert/export_onnx.py:153-387.
+#include "engine.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+
+#include "common.cuh"
+#include "json_min.h"
+
+namespace b200w {
+
+// ---------------------------------------------------------------------------------------------------------
+// weight file
+// ---------------------------------------------------------------------------------------------------------
+void WeightFile::load(const std::string& path) {
+  std::ifstream f(path, std::ios::binary | std::ios::ate);
+  if (!f) throw std::runtime_error("cannot open weight file: " + path);
+  const size_t size = (size_t)f.tellg();
+  f.seekg(0);
+  blob.resize(size);
+  f.read(reinterpret_cast<char*>(blob.data()), (std::streamsize)size);
+  if (size < 12 || memcmp(blob.data(), "B200W001", 8) != 0) throw std::runtime_error("bad weight file magic: " + path);
+  size_t pos = 8;
+  auto rd32 = [&]() {
+    if (pos + 4 > size) throw std::runtime_error("truncated weight file: " + path);
+    uint32_t v;
+    memcpy(&v, blob.data() + pos, 4);
+    pos += 4;
+    return v;
+  };
+  auto rd64 = [&]() {
+    if (pos + 8 > size) throw std::runtime_error("truncated weight file: " + path);
+    uint64_t v;
+    memcpy(&v, blob.data() + pos, 8);
+    pos += 8;
+    return v;
+  };
+  const uint32_t n = rd32();
+  for (uint32_t i = 0; i < n; ++i) {
+    const uint32_t nl = rd32();
+    if (pos + nl > size) throw std::runtime_error("truncated weight file: " + path);
+    std::string name(reinterpret_cast<const char*>(blob.data() + pos), nl);
+    pos += nl;
+    const uint32_t dtype = rd32(), ndim = rd32();
+    if (dtype != 0 || ndim > 4) throw std::runtime_error("unsupported tensor in weight file: " + name);
+    HostTensor t;
+    for (uint32_t k = 0; k < ndim; ++k) t.dims.push_back((size_t)rd64());
+    const uint64_t off = rd64(), nbytes = rd64();
+    if (off + nbytes > size || nbytes != t.numel() * 4) throw std::runtime_error("bad tensor extent in weight file: " + name);
+    t.data = reinterpret_cast<const float*>(blob.data() + off);
+    tensors[name] = t;
+  }
+}
+const HostTensor& WeightFile::get(const std::string& name) const {
+  auto it = tensors.find(name);
+  if (it == tensors.end()) throw std::runtime_error("missing tensor in weight file: " + name);
+  return it->second;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+inline uint16_t f32_to_bf16_rne(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7f800000u) == 0x7f800000u) return (uint16_t)(u >> 16);  // inf / nan
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+template <class T>
+T* dev_alloc(std::vector<void*>& owner, size_t n, bool zero = true) {
+  void* p = nullptr;
+  CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+  if (zero) CUDA_CHECK(cudaMemset(p, 0, std::max<size_t>(n, 1) * sizeof(T)));
+  owner.push_back(p);
+  return reinterpret_cast<T*>(p);
+}
+
+float* upload_f32(std::vector<void*>& owner, const float* src, size_t n) {
+  float* d = dev_alloc<float>(owner, n, false);
+  CUDA_CHECK(cudaMemcpy(d, src, n * sizeof(float), cudaMemcpyHostToDevice));
+  return d;
+}
+__nv_bfloat16* upload_bf16(std::vector<void*>& owner, const std::vector<float>& src, size_t pad_to = 0) {
+  const size_t n = std::max(src.size(), pad_to);
+  std::vector<uint16_t> h(n, 0);
+  for (size_t i = 0; i < src.size(); ++i) h[i] = f32_to_bf16_rne(src[i]);
+  __nv_bfloat16* d = dev_alloc<__nv_bfloat16>(owner, n, false);
+  CUDA_CHECK(cudaMemcpy(d, h.data(), n * 2, cudaMemcpyHostToDevice));
+  return d;
+}
+std::vector<float> to_vec(const HostTensor& t) { return std::vector<float>(t.data, t.data + t.numel()); }
+void append(std::vector<float>& dst, const HostTensor& t) { dst.insert(dst.end(), t.data, t.data + t.numel()); }
+
+std::vector<std::string> split_csv(const std::string& s) {
+  std::vector<std::string> out;
+  std::stringstream ss(s);
+  std::string tok;
+  while (std::getline(ss, tok, ',')) out.push_back(tok);
+  return out;
+}
+
+}  // namespace
+
+struct Engine::LayerEnc {
+  float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  __nv_bfloat16 *w_qkv, *w_out, *w_fc1, *w_fc2;
+  float *b_qkv, *b_out, *b_fc1, *b_fc2;
+};
+struct Engine::LayerDec {
+  float *ln1_g, *ln1_b, *lnx_g, *lnx_b, *ln2_g, *ln2_b;
+  __nv_bfloat16 *w_qkv, *w_out, *w_cq, *w_co, *w_fc1, *w_fc2;
+  float *b_qkv, *b_out, *b_cq, *b_co, *b_fc1, *b_fc2;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// construction / loading
+// ---------------------------------------------------------------------------------------------------------
+Engine::Engine(const std::string& model_root, const std::string& model_type, int device, int max_batch) : device_(device) {
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0)
+    throw CudaError("no CUDA device available: this engine has no CPU path (cudaGetDeviceCount: " + std::string(cudaGetErrorString(e)) + ")");
+  if (device < 0 || device >= n_dev) throw CudaError("invalid CUDA device index");
+  CUDA_CHECK(cudaSetDevice(device_));
+  cudaDeviceProp prop;
+  CUDA_CHECK(cudaGetDeviceProperties(&prop, device_));
+  if (prop.major != 10) throw CudaError(std::string("this build contains sm_100a code only; device is ") + prop.name);
+  CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&pinned_flags_), 4096 * sizeof(int)));
+
+  // directory convention of the reference: {root}/{type}/{type}-*.{...}   (Whisper.cpp:87-90)
+  const std::string dir = model_root + "/" + model_type;
+  const std::string cfg_path = dir + "/" + model_type + "_config.json";
+  std::ifstream cf(cfg_path);
+  if (!cf) throw std::runtime_error("Cannot open config file: " + cfg_path);
+  std::stringstream ss;
+  ss << cf.rdbuf();
+  const JsonFlat j = parse_flat_json(ss.str());
+  cfg_.n_mels = j.get_int("n_mels");
+  cfg_.n_vocab = j.get_int("n_vocab");
+  cfg_.d = j.get_int("n_text_state");
+  cfg_.n_text_ctx = j.get_int("n_text_ctx");
+  cfg_.l_dec = j.get_int("n_text_layer");
+  cfg_.l_enc = j.get_int("n_audio_layer");
+  cfg_.n_head = j.get_int("n_text_head");
+  cfg_.n_audio_ctx = j.has("n_audio_ctx") ? j.get_int("n_audio_ctx") : kAudioCtx;
+  cfg_.sot = j.get_int("sot");
+  cfg_.eot = j.get_int("eot");
+  cfg_.transcribe = j.get_int("transcribe");
+  cfg_.no_timestamps = j.get_int("no_timestamps");
+  for (const std::string& t : split_csv(j.get_str("all_language_tokens"))) cfg_.lang_tokens.push_back(std::stoi(t));
+  cfg_.lang_codes = split_csv(j.get_str("all_language_codes"));
+  if (cfg_.lang_tokens.size() != cfg_.lang_codes.size()) throw std::runtime_error("config: language token / code lists differ in length");
+  if (j.get_int("n_audio_state") != cfg_.d || j.get_int("n_audio_head") != cfg_.n_head)
+    throw std::runtime_error("config: encoder and decoder widths differ (unsupported)");
+  if (cfg_.d != cfg_.n_head * 64) throw std::runtime_error("config: head_dim must be 64");
+  if (cfg_.n_text_ctx != kTextCtx || cfg_.n_audio_ctx != kAudioCtx) throw std::runtime_error("config: unexpected context sizes");
+  if (cfg_.n_mels != 80 && cfg_.n_mels != 128) throw std::runtime_error("config: n_mels must be 80 or 128");
+
+  logmel_upload_tables();
+  kernels_set_attributes();
+  load_weights(dir, model_type);
+  ensure_capacity(std::max(1, max_batch));
+}
+
+Engine::~Engine() {
+  cudaSetDevice(device_);
+  cudaStreamSynchronize(stream_);
+  for (auto& kv : graphs_) cudaGraphExecDestroy(kv.second);
+  free_workspace();
+  for (void* p : owned_) cudaFree(p);
+  if (pinned_flags_) cudaFreeHost(pinned_flags_);
+  if (stream_) cudaStreamDestroy(stream_);
+}
+
+void Engine::load_weights(const std::string& dir, const std::string& type) {
+  WeightFile fe, fd;
+  fe.load(dir + "/" + type + "-encoder.b200w");
+  fd.load(dir + "/" + type + "-decoder.b200w");
+  const int d = cfg_.d, n_mels = cfg_.n_mels;
+  auto check = [](const HostTensor& t, std::initializer_list<size_t> dims, const char* name) {
+    if (t.dims != std::vector<size_t>(dims)) throw std::runtime_error(std::string("unexpected shape for ") + name);
+  };
+  // conv weights [d][C][3] -> [d][3][C] so that a tap is a contiguous K slice
+  auto conv_reorder = [&](const HostTensor& t, int C) {
+    std::vector<float> out((size_t)d * 3 * C);
+    for (int o = 0; o < d; ++o)
+      for (int c = 0; c < C; ++c)
+        for (int k = 0; k < 3; ++k) out[((size_t)o * 3 + k) * C + c] = t.data[((size_t)o * C + c) * 3 + k];
+    return out;
+  };
+  {
+    const HostTensor& w1 = fe.get("encoder.conv1.weight");
+    check(w1, {(size_t)d, (size_t)n_mels, 3}, "encoder.conv1.weight");
+    w_conv1_ = upload_bf16(owned_, conv_reorder(w1, n_mels));
+    b_conv1_ = upload_f32(owned_, fe.get("encoder.conv1.bias").data, d);
+    const HostTensor& w2 = fe.get("encoder.conv2.weight");
+    check(w2, {(size_t)d, (size_t)d, 3}, "encoder.conv2.weight");
+    w_conv2_ = upload_bf16(owned_, conv_reorder(w2, d));
+    b_conv2_ = upload_f32(owned_, fe.get("encoder.conv2.bias").data, d);
+  }
+  {  // sinusoids(1500, d), whisper/model.py
+    std::vector<float> pos((size_t)kAudioCtx * d);
+    const int half = d / 2;
+    const float inc = logf(10000.0f) / (float)(half - 1);
+    for (int t = 0; t < kAudioCtx; ++t)
+      for (int i = 0; i < half; ++i) {
+        const float inv = expf(-inc * (float)i);
+        const float a = (float)t * inv;
+        pos[(size_t)t * d + i] = sinf(a);
+        pos[(size_t)t * d + half + i] = cosf(a);
+      }
+    pos_audio_ = upload_f32(owned_, pos.data(), pos.size());
+  }
+  auto qkv_pack = [&](const WeightFile& f, const std::string& p, __nv_bfloat16** w, float** b) {
+    std::vector<float> wq;
+    append(wq, f.get(p + ".query.weight"));
+    append(wq, f.get(p + ".key.weight"));
+    append(wq, f.get(p + ".value.weight"));
+    std::vector<float> bq(3 * (size_t)d, 0.f);
+    memcpy(bq.data(), f.get(p + ".query.bias").data, d * 4);
+    memcpy(bq.data() + 2 * d, f.get(p + ".value.bias").data, d * 4);  // key has no bias
+    *w = upload_bf16(owned_, wq);
+    *b = upload_f32(owned_, bq.data(), bq.size());
+  };
+  enc_.resize(cfg_.l_enc);
+  for (int i = 0; i < cfg_.l_enc; ++i) {
+    const std::string p = "encoder.blocks." + std::to_string(i);
+    LayerEnc& L = enc_[i];
+    L.ln1_g = upload_f32(owned_, fe.get(p + ".attn_ln.weight").data, d);
+    L.ln1_b = upload_f32(owned_, fe.get(p + ".attn_ln.bias").data, d);
+    qkv_pack(fe, p + ".attn", &L.w_qkv, &L.b_qkv);
+    L.w_out = upload_bf16(owned_, to_vec(fe.get(p + ".attn.out.weight")));
+    L.b_out = upload_f32(owned_, fe.get(p + ".attn.out.bias").data, d);
+    L.ln2_g = upload_f32(owned_, fe.get(p + ".mlp_ln.weight").data, d);
+    L.ln2_b = upload_f32(owned_, fe.get(p + ".mlp_ln.bias").data, d);
+    L.w_fc1 = upload_bf16(owned_, to_vec(fe.get(p + ".mlp.0.weight")));
+    L.b_fc1 = upload_f32(owned_, fe.get(p + ".mlp.0.bias").data, 4 * d);
+    L.w_fc2 = upload_bf16(owned_, to_vec(fe.get(p + ".mlp.2.weight")));
+    L.b_fc2 = upload_f32(owned_, fe.get(p + ".mlp.2.bias").data, d);
+  }
+  ln_post_g_ = upload_f32(owned_, fe.get("encoder.ln_post.weight").data, d);
+  ln_post_b_ = upload_f32(owned_, fe.get("encoder.ln_post.bias").data, d);
+  {  // stacked cross K/V projections: row (layer*2 + kv)*d + out_feature
+    std::vector<float> w, b((size_t)cfg_.l_dec * 2 * d, 0.f);
+    for (int l = 0; l < cfg_.l_dec; ++l) {
+      const std::string p = "decoder.blocks." + std::to_string(l) + ".cross_attn";
+      append(w, fe.get(p + ".key.weight"));
+      append(w, fe.get(p + ".value.weight"));
+      memcpy(b.data() + ((size_t)l * 2 + 1) * d, fe.get(p + ".value.bias").data, d * 4);
+    }
+    w_crosskv_ = upload_bf16(owned_, w);
+    b_crosskv_ = upload_f32(owned_, b.data(), b.size());
+  }
+  dec_.resize(cfg_.l_dec);
+  for (int i = 0; i < cfg_.l_dec; ++i) {
+    const std::string p = "decoder.blocks." + std::to_string(i);
+    LayerDec& L = dec_[i];
+    L.ln1_g = upload_f32(owned_, fd.get(p + ".attn_ln.weight").data, d);
+    L.ln1_b = upload_f32(owned_, fd.get(p + ".attn_ln.bias").data, d);
+    qkv_pack(fd, p + ".attn", &L.w_qkv, &L.b_qkv);
+    L.w_out = upload_bf16(owned_, to_vec(fd.get(p + ".attn.out.weight")));
+    L.b_out = upload_f32(owned_, fd.get(p + ".attn.out.bias").data, d);
+    L.lnx_g = upload_f32(owned_, fd.get(p + ".cross_attn_ln.weight").data, d);
+    L.lnx_b = upload_f32(owned_, fd.get(p + ".cross_attn_ln.bias").data, d);
+    L.w_cq = upload_bf16(owned_, to_vec(fd.get(p + ".cross_attn.query.weight")));
+    L.b_cq = upload_f32(owned_, fd.get(p + ".cross_attn.query.bias").data, d);
+    L.w_co = upload_bf16(owned_, to_vec(fd.get(p + ".cross_attn.out.weight")));
+    L.b_co = upload_f32(owned_, fd.get(p + ".cross_attn.out.bias").data, d);
+    L.ln2_g = upload_f32(owned_, fd.get(p + ".mlp_ln.weight").data, d);
+    L.ln2_b = upload_f32(owned_, fd.get(p + ".mlp_ln.bias").data, d);
+    L.w_fc1 = upload_bf16(owned_, to_vec(fd.get(p + ".mlp.0.weight")));
+    L.b_fc1 = upload_f32(owned_, fd.get(p + ".mlp.0.bias").data, 4 * d);
+    L.w_fc2 = upload_bf16(owned_, to_vec(fd.get(p + ".mlp.2.weight")));
+    L.b_fc2 = upload_f32(owned_, fd.get(p + ".mlp.2.bias").data, d);
+  }
+  dec_ln_g_ = upload_f32(owned_, fd.get("decoder.ln.weight").data, d);
+  dec_ln_b_ = upload_f32(owned_, fd.get("decoder.ln.bias").data, d);
+  const HostTensor& emb = fd.get("decoder.token_embedding.weight");
+  check(emb, {(size_t)cfg_.n_vocab, (size_t)d}, "decoder.token_embedding.weight");
+  vocab_pad_ = (cfg_.n_vocab + 255) / 256 * 256;  // zero rows so every W tile is in bounds
+  emb_f32_ = upload_f32(owned_, emb.data, emb.numel());
+  w_emb_bf16_ = upload_bf16(owned_, to_vec(emb), (size_t)vocab_pad_ * d);
+  const HostTensor& pe = fd.get("decoder.positional_embedding");
+  check(pe, {(size_t)kTextCtx, (size_t)d}, "decoder.positional_embedding");
+  pos_text_ = upload_f32(owned_, pe.data, pe.numel());
+}
+
+std::vector<int> Engine::sot_sequence(const std::string& lang, std::string* resolved) const {
+  // Whisper::get_lang_token, Whisper.cpp:241-251: unknown language falls back to DEFAULT_LANG "zh"
+  std::string l = lang;
+  auto it = std::find(cfg_.lang_codes.begin(), cfg_.lang_codes.end(), l);
+  if (it == cfg_.lang_codes.end()) {
+    l = "zh";
+    it = std::find(cfg_.lang_codes.begin(), cfg_.lang_codes.end(), l);
+    if (it == cfg_.lang_codes.end()) throw std::runtime_error("config has no language 'zh' to fall back to");
+  }
+  if (resolved) *resolved = l;
+  return {cfg_.sot, cfg_.lang_tokens[it - cfg_.lang_codes.begin()], cfg_.transcribe, cfg_.no_timestamps};
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// workspace + plans
+// ---------------------------------------------------------------------------------------------------------
+void Engine::free_workspace() {
+  for (auto& kv : graphs_) cudaGraphExecDestroy(kv.second);
+  graphs_.clear();
+  for (GemmPlan* p : plans_) gemm_plan_destroy(p);
+  plans_.clear();
+  enc_plans_.clear();
+  dec_plans_.clear();
+  for (void* p : ws_owned_) cudaFree(p);
+  ws_owned_.clear();
+}
+
+void Engine::ensure_capacity(int B, long max_samples) {
+  const long stride = std::max<long>(kChunkSamples, (max_samples + 7) / 8 * 8);
+  if (B <= cap_ && stride <= pcm_stride_) return;
+  CUDA_CHECK(cudaSetDevice(device_));
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+  free_workspace();
+  cap_ = std::max(B, cap_);
+  pcm_stride_ = std::max(stride, pcm_stride_);
+  const int d = cfg_.d, H = cfg_.n_head, L = cfg_.l_dec;
+  const char* sub_env = getenv("B200W_ENC_SUB_BATCH");
+  enc_sub_ = std::min(cap_, sub_env ? std::max(1, atoi(sub_env)) : 32);
+  const size_t rows_sub = (size_t)enc_sub_ * kAudioCtx;
+  auto& o = ws_owned_;
+  pcm_ = dev_alloc<float>(o, (size_t)cap_ * pcm_stride_, false);
+  n_samples_ = dev_alloc<int>(o, cap_);
+  utt_max_ = dev_alloc<float>(o, cap_);
+  mel_ = dev_alloc<float>(o, (size_t)cap_ * cfg_.n_mels * kMelFrames);
+  mel_tm_ = dev_alloc<__nv_bfloat16>(o, (size_t)cap_ * (kMelFrames + 2) * cfg_.n_mels);
+  conv1_out_ = dev_alloc<__nv_bfloat16>(o, (size_t)enc_sub_ * (kMelFrames + 2) * d);
+  x_enc_ = dev_alloc<float>(o, rows_sub * d);
+  h_enc_ = dev_alloc<__nv_bfloat16>(o, rows_sub * d);
+  qkv_enc_ = dev_alloc<__nv_bfloat16>(o, rows_sub * 3 * d);
+  attn_enc_ = dev_alloc<__nv_bfloat16>(o, rows_sub * d);
+  mlp_enc_ = dev_alloc<__nv_bfloat16>(o, rows_sub * 4 * d);
+  const size_t ckv = (size_t)L * cap_ * H * kAudioCtx * 64;
+  cross_k_ = dev_alloc<__nv_bfloat16>(o, ckv, false);
+  cross_v_ = dev_alloc<__nv_bfloat16>(o, ckv, false);
+  const size_t skv = (size_t)L * cap_ * H * kTextCtx * 64;
+  self_k_ = dev_alloc<__nv_bfloat16>(o, skv);
+  self_v_ = dev_alloc<__nv_bfloat16>(o, skv);
+  dec_rows_pad_ = (cap_ + 127) / 128 * 128;
+  x_dec_ = dev_alloc<float>(o, (size_t)dec_rows_pad_ * d);
+  qkv_dec_ = dev_alloc<float>(o, (size_t)dec_rows_pad_ * 3 * d);
+  q_dec_ = dev_alloc<float>(o, (size_t)dec_rows_pad_ * d);
+  h_dec_ = dev_alloc<__nv_bfloat16>(o, (size_t)dec_rows_pad_ * d);
+  attn_dec_ = dev_alloc<__nv_bfloat16>(o, (size_t)dec_rows_pad_ * d);
+  mlp_dec_ = dev_alloc<__nv_bfloat16>(o, (size_t)dec_rows_pad_ * 4 * d);
+  logits_ = dev_alloc<float>(o, (size_t)cap_ * vocab_pad_);
+  logits_tiles_ = vocab_pad_ / 128;
+  part_val_ = dev_alloc<float>(o, (size_t)cap_ * logits_tiles_);
+  part_idx_ = dev_alloc<int>(o, (size_t)cap_ * logits_tiles_);
+  const size_t np = (size_t)cap_ * H * 8;
+  part_m_ = dev_alloc<float>(o, np);
+  part_l_ = dev_alloc<float>(o, np);
+  part_o_ = dev_alloc<float>(o, np * 64);
+  st_.step = dev_alloc<int>(o, 1);
+  st_.tokens = dev_alloc<int>(o, (size_t)cap_ * kTextCtx);
+  st_.forced = dev_alloc<int>(o, (size_t)cap_ * kTextCtx);
+  st_.finished = dev_alloc<int>(o, cap_);
+  st_.n_generated = dev_alloc<int>(o, cap_);
+  st_.out_tokens = dev_alloc<int>(o, (size_t)cap_ * kTextCtx);
+  st_.margins = nullptr;
+  build_plans();
+}
+
+void Engine::build_plans() {
+  const int d = cfg_.d, n_mels = cfg_.n_mels;
+  auto keep = [&](GemmPlan* p) {
+    plans_.push_back(p);
+    return p;
+  };
+  auto flat = [&](const __nv_bfloat16* ptr, int K, int rows) {
+    GemmOperandA a{};
+    a.ptr = ptr, a.K = K, a.rows = rows, a.n_batch = 1, a.row_pitch = K, a.batch_pitch = (long)rows * K, a.n_taps = 0;
+    return a;
+  };
+  {  // conv1: x_pad [cap][3002][n_mels], taps = rows +0,+1,+2 (padded row index = t + tap)
+    GemmOperandA a{};
+    a.ptr = mel_tm_, a.K = n_mels, a.rows = kMelFrames + 2, a.n_batch = cap_, a.row_pitch = n_mels;
+    a.batch_pitch = (long)(kMelFrames + 2) * n_mels;
+    a.n_taps = 3, a.k_per_tap = n_mels;
+    for (int t = 0; t < 3; ++t) a.tap_c0[t] = 0, a.tap_row[t] = t;
+    p_conv1_ = keep(gemm_plan_create(a, w_conv1_, d, 128, EPI_BIAS_GELU_BF16));
+  }
+  {  // conv2 (stride 2): conv1_out viewed as [sub][1501][2d]; out t reads padded rows 2t, 2t+1, 2t+2
+    GemmOperandA a{};
+    a.ptr = conv1_out_, a.K = 2 * d, a.rows = (kMelFrames + 2) / 2, a.n_batch = enc_sub_, a.row_pitch = 2L * d;
+    a.batch_pitch = (long)(kMelFrames + 2) * d;
+    a.n_taps = 3, a.k_per_tap = d;
+    a.tap_c0[0] = 0, a.tap_row[0] = 0;
+    a.tap_c0[1] = d, a.tap_row[1] = 0;
+    a.tap_c0[2] = 0, a.tap_row[2] = 1;
+    p_conv2_ = keep(gemm_plan_create(a, w_conv2_, d, 128, EPI_GELU_POS_F32));
+  }
+  const int rows_sub = enc_sub_ * kAudioCtx;
+  enc_plans_.resize(cfg_.l_enc);
+  for (int i = 0; i < cfg_.l_enc; ++i) {
+    const LayerEnc& L = enc_[i];
+    enc_plans_[i].qkv = keep(gemm_plan_create(flat(h_enc_, d, rows_sub), L.w_qkv, 3 * d, 256, EPI_BIAS_BF16));
+    enc_plans_[i].out = keep(gemm_plan_create(flat(attn_enc_, d, rows_sub), L.w_out, d, 128, EPI_BIAS_RESID_F32));
+    enc_plans_[i].fc1 = keep(gemm_plan_create(flat(h_enc_, d, rows_sub), L.w_fc1, 4 * d, 256, EPI_BIAS_GELU_BF16));
+    enc_plans_[i].fc2 = keep(gemm_plan_create(flat(mlp_enc_, 4 * d, rows_sub), L.w_fc2, d, 128, EPI_BIAS_RESID_F32));
+  }
+  {  // cross K/V: rows are (chunk, t) so the epilogue can scatter head-major per chunk
+    GemmOperandA a{};
+    a.ptr = h_enc_, a.K = d, a.rows = kAudioCtx, a.n_batch = enc_sub_, a.row_pitch = d, a.batch_pitch = (long)kAudioCtx * d, a.n_taps = 0;
+    p_crosskv_ = keep(gemm_plan_create(a, w_crosskv_, 2 * cfg_.l_dec * d, 256, EPI_CROSSKV_BF16));
+  }
+  dec_plans_.resize(cfg_.l_dec);
+  const int bn = 64;
+  for (int i = 0; i < cfg_.l_dec; ++i) {
+    const LayerDec& L = dec_[i];
+    dec_plans_[i].qkv = keep(gemm_plan_create(flat(h_dec_, d, dec_rows_pad_), L.w_qkv, 3 * d, bn, EPI_BIAS_F32));
+    dec_plans_[i].out = keep(gemm_plan_create(flat(attn_dec_, d, dec_rows_pad_), L.w_out, d, bn, EPI_BIAS_RESID_F32));
+    dec_plans_[i].cq = keep(gemm_plan_create(flat(h_dec_, d, dec_rows_pad_), L.w_cq, d, bn, EPI_BIAS_F32));
+    dec_plans_[i].co = keep(gemm_plan_create(flat(attn_dec_, d, dec_rows_pad_), L.w_co, d, bn, EPI_BIAS_RESID_F32));
+    dec_plans_[i].fc1 = keep(gemm_plan_create(flat(h_dec_, d, dec_rows_pad_), L.w_fc1, 4 * d, bn, EPI_BIAS_GELU_BF16));
+    dec_plans_[i].fc2 = keep(gemm_plan_create(flat(mlp_dec_, 4 * d, dec_rows_pad_), L.w_fc2, d, bn, EPI_BIAS_RESID_F32));
+  }
+  p_logits_ = keep(gemm_plan_create(flat(h_dec_, d, dec_rows_pad_), w_emb_bf16_, vocab_pad_, 128, EPI_ARGMAX));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// stages
+// ---------------------------------------------------------------------------------------------------------
+void Engine::run_logmel(int B, int max_samples) {
+  launch_logmel(pcm_, pcm_stride_, n_samples_, max_samples, B, cfg_.n_mels, mel_, mel_tm_, utt_max_, stream_);
+  launches_ += 3;
+}
+void Engine::run_mel_convert(int B) {
+  launch_mel_to_timemajor(mel_, B, cfg_.n_mels, mel_tm_, stream_);
+  launches_ += 1;
+}
+
+void Engine::run_encoder(int B) {
+  const int d = cfg_.d, H = cfg_.n_head;
+  for (int b0 = 0; b0 < B; b0 += enc_sub_) {
+    const int nb = std::min(enc_sub_, B - b0);
+    const int rows = nb * kAudioCtx;
+    GemmParams p{};
+    // conv1 + GELU -> padded bf16 [nb][3002][d] (row t+1)
+    p = GemmParams{};
+    p.rows_valid = kMelFrames, p.N = d, p.out = conv1_out_, p.ldo = d, p.out_batch_pitch = (long)(kMelFrames + 2) * d;
+    p.out_row_offset = 1, p.a_batch_offset = b0, p.n_batch = nb, p.bias = b_conv1_;
+    gemm_launch(p_conv1_, p, stream_);
+    // conv2 (stride 2) + GELU + positional embedding -> residual stream f32 [nb*1500][d]
+    p = GemmParams{};
+    p.rows_valid = kAudioCtx, p.N = d, p.out = x_enc_, p.ldo = d, p.out_batch_pitch = (long)kAudioCtx * d;
+    p.n_batch = nb, p.bias = b_conv2_, p.pos = pos_audio_;
+    gemm_launch(p_conv2_, p, stream_);
+    launches_ += 2;
+    for (int i = 0; i < cfg_.l_enc; ++i) {
+      const LayerEnc& L = enc_[i];
+      launch_layernorm(x_enc_, L.ln1_g, L.ln1_b, h_enc_, rows, d, stream_);
+      p = GemmParams{};
+      p.rows_valid = rows, p.N = 3 * d, p.out = qkv_enc_, p.ldo = 3 * d, p.bias = L.b_qkv, p.n_batch = 1;
+      gemm_launch(enc_plans_[i].qkv, p, stream_);
+      launch_encoder_attention(qkv_enc_, attn_enc_, nb, kAudioCtx, H, stream_);
+      p = GemmParams{};
+      p.rows_valid = rows, p.N = d, p.out = x_enc_, p.ldo = d, p.bias = L.b_out, p.n_batch = 1;
+      gemm_launch(enc_plans_[i].out, p, stream_);
+      launch_layernorm(x_enc_, L.ln2_g, L.ln2_b, h_enc_, rows, d, stream_);
+      p = GemmParams{};
+      p.rows_valid = rows, p.N = 4 * d, p.out = mlp_enc_, p.ldo = 4 * d, p.bias = L.b_fc1, p.n_batch = 1;
+      gemm_launch(enc_plans_[i].fc1, p, stream_);
+      p = GemmParams{};
+      p.rows_valid = rows, p.N = d, p.out = x_enc_, p.ldo = d, p.bias = L.b_fc2, p.n_batch = 1;
+      gemm_launch(enc_plans_[i].fc2, p, stream_);
+      launches_ += 7;
+    }
+    launch_layernorm(x_enc_, ln_post_g_, ln_post_b_, h_enc_, rows, d, stream_);
+    p = GemmParams{};
+    p.rows_valid = kAudioCtx, p.N = 2 * cfg_.l_dec * d, p.n_batch = nb, p.bias = b_crosskv_;
+    p.cross_k = cross_k_, p.cross_v = cross_v_, p.d_model = d, p.n_head = H, p.n_ctx_kv = kAudioCtx, p.kv_batch = cap_, p.kv_batch_offset = b0;
+    gemm_launch(p_crosskv_, p, stream_);
+    launches_ += 2;
+  }
+}
+
+void Engine::enqueue_decode_step(int B, bool want_logits) {
+  const int d = cfg_.d, H = cfg_.n_head;
+  const int n_split = cross_attention_pick_split(B, H);
+  launch_embed(st_, emb_f32_, pos_text_, x_dec_, B, d, kTextCtx, stream_);
+  launches_ += 1;
+  GemmParams p{};
+  auto gp = [&](void* out, long ldo, int N, const float* bias) {
+    GemmParams q{};
+    q.rows_valid = B, q.N = N, q.out = out, q.ldo = ldo, q.bias = bias, q.n_batch = 1;
+    return q;
+  };
+  for (int l = 0; l < cfg_.l_dec; ++l) {
+    const LayerDec& L = dec_[l];
+    const DecPlans& P = dec_plans_[l];
+    const size_t skv_off = (size_t)l * cap_ * H * kTextCtx * 64;
+    const size_t ckv_off = (size_t)l * cap_ * H * kAudioCtx * 64;
+    launch_layernorm(x_dec_, L.ln1_g, L.ln1_b, h_dec_, B, d, stream_);
+    gemm_launch(P.qkv, gp(qkv_dec_, 3 * d, 3 * d, L.b_qkv), stream_);
+    launch_self_attention_decode(qkv_dec_, self_k_ + skv_off, self_v_ + skv_off, st_.step, attn_dec_, B, H, kTextCtx, stream_);
+    gemm_launch(P.out, gp(x_dec_, d, d, L.b_out), stream_);
+    launch_layernorm(x_dec_, L.lnx_g, L.lnx_b, h_dec_, B, d, stream_);
+    gemm_launch(P.cq, gp(q_dec_, d, d, L.b_cq), stream_);
+    launch_cross_attention_decode(q_dec_, cross_k_ + ckv_off, cross_v_ + ckv_off, attn_dec_, B, H, kAudioCtx, n_split, part_m_, part_l_,
+                                  part_o_, stream_);
+    gemm_launch(P.co, gp(x_dec_, d, d, L.b_co), stream_);
+    launch_layernorm(x_dec_, L.ln2_g, L.ln2_b, h_dec_, B, d, stream_);
+    gemm_launch(P.fc1, gp(mlp_dec_, 4 * d, 4 * d, L.b_fc1), stream_);
+    gemm_launch(P.fc2, gp(x_dec_, d, d, L.b_fc2), stream_);
+    launches_ += 11 + (n_split > 1 ? 1 : 0);
+  }
+  launch_layernorm(x_dec_, dec_ln_g_, dec_ln_b_, h_dec_, B, d, stream_);
+  p = gp(want_logits ? logits_ : nullptr, vocab_pad_, cfg_.n_vocab, nullptr);
+  p.part_val = part_val_, p.part_idx = part_idx_, p.part_ld = logits_tiles_;
+  gemm_launch(p_logits_, p, stream_);
+  launches_ += 2;
+}
+
+void Engine::decode_reset(int B) {
+  CUDA_CHECK(cudaMemsetAsync(st_.step, 0, sizeof(int), stream_));
+  CUDA_CHECK(cudaMemsetAsync(st_.finished, 0, sizeof(int) * B, stream_));
+  CUDA_CHECK(cudaMemsetAsync(st_.forced, 0xff, sizeof(int) * (size_t)B * kTextCtx, stream_));  // -1
+}
+
+int Engine::run_decode(int B, const std::vector<int>& sot, const DecodeOptions& opt, std::vector<std::vector<int>>* tokens) {
+  if ((int)sot.size() != kSotLen) throw std::runtime_error("sot sequence must have 4 tokens");
+  CUDA_CHECK(cudaSetDevice(device_));
+  decode_reset(B);
+  // prefill token / forcing tables
+  std::vector<int> tok((size_t)B * kTextCtx, 0), forced((size_t)B * kTextCtx, -1);
+  for (int b = 0; b < B; ++b) {
+    for (int i = 0; i < kSotLen; ++i) tok[(size_t)b * kTextCtx + i] = sot[i];
+    for (int i = 0; i < opt.forced_len && kSotLen + i < kTextCtx; ++i)
+      forced[(size_t)b * kTextCtx + kSotLen + i] = opt.forced_tokens[(size_t)b * opt.forced_len + i];
+  }
+  CUDA_CHECK(cudaMemcpyAsync(st_.tokens, tok.data(), tok.size() * sizeof(int), cudaMemcpyHostToDevice, stream_));
+  if (opt.forced_tokens)
+    CUDA_CHECK(cudaMemcpyAsync(st_.forced, forced.data(), forced.size() * sizeof(int), cudaMemcpyHostToDevice, stream_));
+  CUDA_CHECK(cudaStreamSynchronize(stream_));  // tok/forced are stack-owned host vectors
+
+  // number of decoder runs: 4 SOT steps + one per generated token (each generated token is fed back, Whisper.cpp:219-222)
+  const int max_new = std::max(1, std::min(opt.max_new_tokens, kTextCtx - kSotLen));
+  const int n_steps = kSotLen + max_new;  // like the reference, the last token is fed back too and its result discarded
+  const bool want_logits = opt.logits_out != nullptr;
+  const bool graph = opt.use_graph && !want_logits && getenv("B200W_NO_GRAPH") == nullptr;
+  cudaGraphExec_t exec = nullptr;
+  if (graph) {
+    const int key = B * 2 + (opt.honor_eot ? 1 : 0);
+    auto it = graphs_.find(key);
+    if (it == graphs_.end()) {
+      cudaGraph_t g;
+      CUDA_CHECK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+      const long before = launches_;
+      enqueue_decode_step(B, false);
+      launch_argmax_finalize(st_, part_val_, part_idx_, logits_tiles_, logits_tiles_, B, kTextCtx, cfg_.eot, opt.honor_eot ? 1 : 0, kSotLen, stream_);
+      launches_ = before;  // capture does not launch
+      CUDA_CHECK(cudaStreamEndCapture(stream_, &g));
+      CUDA_CHECK(cudaGraphInstantiate(&exec, g, 0));
+      CUDA_CHECK(cudaGraphDestroy(g));
+      graphs_[key] = exec;
+    } else {
+      exec = it->second;
+    }
+  }
+  const int n_split = cross_attention_pick_split(B, cfg_.n_head);
+  const long per_step = 1 + (long)cfg_.l_dec * (11 + (n_split > 1 ? 1 : 0)) + 2 + 2;
+  int steps_done = 0;
+  for (int s = 0; s < n_steps; ++s) {
+    if (graph) {
+      CUDA_CHECK(cudaGraphLaunch(exec, stream_));
+      launches_ += per_step;
+    } else {
+      enqueue_decode_step(B, want_logits);
+      launch_argmax_finalize(st_, part_val_, part_idx_, logits_tiles_, logits_tiles_, B, kTextCtx, cfg_.eot, opt.honor_eot ? 1 : 0, kSotLen, stream_);
+      launches_ += 2;
+      if (want_logits && s >= kSotLen - 1 && s - (kSotLen - 1) < max_new) {
+        // logits after consuming position s = prediction of generated token (s - 3)
+        CUDA_CHECK(cudaMemcpy2DAsync(opt.logits_out + (size_t)(s - (kSotLen - 1)) * B * cfg_.n_vocab, (size_t)cfg_.n_vocab * 4, logits_,
+                                     (size_t)vocab_pad_ * 4, (size_t)cfg_.n_vocab * 4, B, cudaMemcpyDeviceToHost, stream_));
+      }
+    }
+    ++steps_done;
+    if (opt.honor_eot && (s % 16 == 15) && s + 1 < n_steps) {
+      CUDA_CHECK(cudaMemcpyAsync(pinned_flags_, st_.finished, sizeof(int) * std::min(B, 4096), cudaMemcpyDeviceToHost, stream_));
+      CUDA_CHECK(cudaStreamSynchronize(stream_));
+      bool all = B <= 4096;
+      for (int b = 0; b < std::min(B, 4096) && all; ++b) all = pinned_flags_[b] != 0;
+      if (all) break;
+    }
+  }
+  if (tokens) {
+    std::vector<int> out((size_t)B * kTextCtx);
+    CUDA_CHECK(cudaMemcpyAsync(out.data(), st_.out_tokens, out.size() * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    tokens->assign(B, {});
+    for (int b = 0; b < B; ++b) {
+      // generated token i is the argmax after consuming position 3 + i (Whisper.cpp:214-222)
+      for (int i = 0; i < max_new && kSotLen - 1 + i < steps_done; ++i) {
+        const int t = out[(size_t)b * kTextCtx + kSotLen - 1 + i];
+        if (opt.honor_eot && t == cfg_.eot) break;
+        (*tokens)[b].push_back(t);
+      }
+    }
+  }
+  return steps_done;
+}
+
+void Engine::decode_step_tokens(int B, const int* tokens_host, int offset, float* logits_host, float* this_k, float* this_v) {
+  // one decoder run on the resident caches, driven like the reference's run_decoder(token, offset)
+  CUDA_CHECK(cudaSetDevice(device_));
+  const int d = cfg_.d, H = cfg_.n_head, L = cfg_.l_dec;
+  if (offset < 0 || offset >= kTextCtx) throw std::runtime_error("decoder offset out of range");
+  std::vector<int> col(B);
+  for (int b = 0; b < B; ++b) col[b] = tokens_host[b];
+  CUDA_CHECK(cudaMemcpy2DAsync(st_.tokens + offset, kTextCtx * sizeof(int), col.data(), sizeof(int), sizeof(int), B, cudaMemcpyHostToDevice, stream_));
+  CUDA_CHECK(cudaMemcpyAsync(st_.step, &offset, sizeof(int), cudaMemcpyHostToDevice, stream_));
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+  enqueue_decode_step(B, true);
+  if (logits_host)
+    CUDA_CHECK(cudaMemcpy2DAsync(logits_host, (size_t)cfg_.n_vocab * 4, logits_, (size_t)vocab_pad_ * 4, (size_t)cfg_.n_vocab * 4, B,
+                                 cudaMemcpyDeviceToHost, stream_));
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+  if (this_k || this_v) {
+    // rows just appended to the bf16 caches, returned as f32 [L][B][d]
+    std::vector<uint16_t> tmp(64);
+    for (int kv = 0; kv < 2; ++kv) {
+      float* dst = kv == 0 ? this_k : this_v;
+      if (!dst) continue;
+      const __nv_bfloat16* cache = kv == 0 ? self_k_ : self_v_;
+      for (int l = 0; l < L; ++l)
+        for (int b = 0; b < B; ++b)
+          for (int h = 0; h < H; ++h) {
+            const size_t off = ((((size_t)l * cap_ + b) * H + h) * kTextCtx + offset) * 64;
+            CUDA_CHECK(cudaMemcpy(tmp.data(), cache + off, 128, cudaMemcpyDeviceToHost));
+            for (int i = 0; i < 64; ++i) {
+              uint32_t u = (uint32_t)tmp[i] << 16;
+              float f;
+              memcpy(&f, &u, 4);
+              dst[((size_t)l * B + b) * d + h * 64 + i] = f;
+            }
+          }
+    }
+  }
+}
+
+void Engine::read_cross_kv(int B, float* cross_k, float* cross_v) const {
+  const int d = cfg_.d, H = cfg_.n_head, L = cfg_.l_dec;
+  const size_t per = (size_t)kAudioCtx * 64;
+  std::vector<uint16_t> tmp(per);
+  for (int kv = 0; kv < 2; ++kv) {
+    float* dst = kv == 0 ? cross_k : cross_v;
+    if (!dst) continue;
+    const __nv_bfloat16* src = kv == 0 ? cross_k_ : cross_v_;
+    for (int l = 0; l < L; ++l)
+      for (int b = 0; b < B; ++b)
+        for (int h = 0; h < H; ++h) {
+          CUDA_CHECK(cudaMemcpy(tmp.data(), src + (((size_t)l * cap_ + b) * H + h) * per, per * 2, cudaMemcpyDeviceToHost));
+          for (int t = 0; t < kAudioCtx; ++t)
+            for (int i = 0; i < 64; ++i) {
+              uint32_t u = (uint32_t)tmp[(size_t)t * 64 + i] << 16;
+              float f;
+              memcpy(&f, &u, 4);
+              dst[(((size_t)l * B + b) * kAudioCtx + t) * d + h * 64 + i] = f;
+            }
+        }
+  }
+}
+
+void Engine::read_encoder_hidden(int B, float* out) const {
+  if (B > enc_sub_) throw std::runtime_error("read_encoder_hidden: batch exceeds the encoder sub-batch");
+  CUDA_CHECK(cudaMemcpy(out, x_enc_, (size_t)B * kAudioCtx * cfg_.d * 4, cudaMemcpyDeviceToHost));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// whole pipeline
+// ---------------------------------------------------------------------------------------------------------
+void Engine::transcribe_resident(int B, int max_samples, const std::string& lang, const DecodeOptions& opt,
+                                 std::vector<std::vector<int>>* tokens, StageTimes* times) {
+  CUDA_CHECK(cudaSetDevice(device_));
+  cudaEvent_t ev[4];
+  for (auto& e : ev) CUDA_CHECK(cudaEventCreate(&e));
+  const long l0 = launches_;
+  CUDA_CHECK(cudaEventRecord(ev[0], stream_));
+  run_logmel(B, max_samples);
+  CUDA_CHECK(cudaEventRecord(ev[1], stream_));
+  run_encoder(B);
+  CUDA_CHECK(cudaEventRecord(ev[2], stream_));
+  const int steps = run_decode(B, sot_sequence(lang), opt, tokens);
+  CUDA_CHECK(cudaEventRecord(ev[3], stream_));
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+  if (times) {
+    CUDA_CHECK(cudaEventElapsedTime(&times->mel_ms, ev[0], ev[1]));
+    CUDA_CHECK(cudaEventElapsedTime(&times->encoder_ms, ev[1], ev[2]));
+    CUDA_CHECK(cudaEventElapsedTime(&times->decode_ms, ev[2], ev[3]));
+    CUDA_CHECK(cudaEventElapsedTime(&times->total_ms, ev[0], ev[3]));
+    times->decode_steps = steps;
+    times->kernel_launches = launches_ - l0;
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+}
+
+void Engine::transcribe(const float* const* pcm, const int* n_samples, int B, const std::string& lang, const DecodeOptions& opt,
+                        std::vector<std::vector<int>>* tokens, StageTimes* times) {
+  CUDA_CHECK(cudaSetDevice(device_));
+  int max_samples = 0;
+  for (int b = 0; b < B; ++b) {
+    if (n_samples[b] < 201) throw std::runtime_error("audio shorter than 201 samples (reflect padding needs n_fft/2 + 1)");
+    max_samples = std::max(max_samples, n_samples[b]);
+  }
+  ensure_capacity(B, max_samples);
+  cudaEvent_t e0, e1;
+  CUDA_CHECK(cudaEventCreate(&e0));
+  CUDA_CHECK(cudaEventCreate(&e1));
+  CUDA_CHECK(cudaEventRecord(e0, stream_));
+  for (int b = 0; b < B; ++b)
+    CUDA_CHECK(cudaMemcpyAsync(pcm_ + (size_t)b * pcm_stride_, pcm[b], (size_t)n_samples[b] * 4, cudaMemcpyHostToDevice, stream_));
+  CUDA_CHECK(cudaMemcpyAsync(n_samples_, n_samples, sizeof(int) * B, cudaMemcpyHostToDevice, stream_));
+  CUDA_CHECK(cudaEventRecord(e1, stream_));
+  transcribe_resident(B, max_samples, lang, opt, tokens, times);
+  if (times) {
+    CUDA_CHECK(cudaEventElapsedTime(&times->h2d_ms, e0, e1));
+    times->total_ms += times->h2d_ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+}
+
+}  // namespace b200w

@@ -1,0 +1,473 @@
+// K4: bf16 GEMM on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM, operands staged by TMA).
+//
+//   C[m][n] = sum_k A[m][k] * W[n][k]      A: activations (K-major), W: nn.Linear / Conv1d weight (K-major)
+//
+// This is every dense contraction of the reference's exported graphs
+// (/root/reference/model_convert/export_onnx.py: conv1/conv2 :158-159 as implicit GEMMs over overlapping
+// time windows, attention / MLP projections of the encoder blocks :177-178, cross K/V projections :205-210,
+// every Linear of the decoder step :245-247,:228-230,:298 and the tied logits product :378-385).
+//
+// Structure (one CTA per SM, persistent over output tiles, 192 threads):
+//   warp 0  (1 lane)  TMA producer: A tile 128x64 and W tile BLOCK_Nx64 per k-block, SWIZZLE_128B, kStages ring
+//   warp 1  (1 lane)  MMA issuer: 4 x tcgen05.mma (M=128, N=BLOCK_N, K=16) per k-block into one of two TMEM
+//                     accumulator stages; tcgen05.commit releases smem slots / publishes the accumulator
+//   warps 2-5         epilogue: tcgen05.ld 32 columns at a time (thread = output row), fused bias / GELU /
+//                     residual / positional embedding / head-major scatter / arg-max, direct 16-byte stores
+// Tile order is n-fastest so the CTAs in flight share A row-blocks and the whole W through L2.
+#include <cfloat>
+#include <mutex>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b200w {
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;   // 64 bf16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kGemmThreads = 192;
+constexpr int kSmemBudget = 196608;  // 192 KB of operand stages
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int kStageBytesA = BLOCK_M * BLOCK_K * 2;
+  static constexpr int kStageBytesB = BLOCK_N * BLOCK_K * 2;
+  static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
+  static constexpr int kStages = kSmemBudget / kStageBytes;  // 256 -> 4, 128 -> 6, 64 -> 8, 32 -> 9
+  static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct TileCoord {
+  int batch, m_blk, n_blk;
+};
+
+struct GemmGeom {
+  int m_tiles_per_batch, n_tiles, n_batch, num_k_blocks, total_tiles;
+  // implicit-GEMM convolution: the k loop runs over n_taps shifted views of A (tap t reads A columns
+  // a_c0[t] + k, rows row + a_row[t]) against W columns w_k0[t] + k.  A plain GEMM has one tap.
+  int n_taps, kb_per_tap;
+  int a_c0[3], a_row[3], w_k0[3];
+};
+
+__device__ __forceinline__ TileCoord tile_coord(int t, const GemmGeom& g) {
+  TileCoord c;
+  c.n_blk = t % g.n_tiles;
+  int mt = t / g.n_tiles;
+  c.m_blk = mt % g.m_tiles_per_batch;
+  c.batch = mt / g.m_tiles_per_batch;
+  return c;
+}
+
+template <int BLOCK_N, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmGeom g,
+                    const GemmParams p) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ unsigned char smem_raw[];
+  // SWIZZLE_128B operand tiles need 1024-byte alignment
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_base_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
+        const TileCoord c = tile_coord(t, g);
+        for (int tap = 0; tap < g.n_taps; ++tap) {
+          for (int kb = 0; kb < g.kb_per_tap; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            unsigned char* sa = smem + stage * Cfg::kStageBytes;
+            unsigned char* sb = sa + Cfg::kStageBytesA;
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_3d(sa, &tmap_a, &full_bar[stage], g.a_c0[tap] + kb * BLOCK_K, c.m_blk * BLOCK_M + g.a_row[tap], c.batch + p.a_batch_offset);
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], g.w_k0[tap] + kb * BLOCK_K, c.n_blk * BLOCK_N);
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc_stage = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
+        mbar_wait(&tmem_empty_bar[acc_stage], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + acc_stage * BLOCK_N;
+        for (int kb = 0; kb < g.num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint64_t da = umma_desc_kmajor_sw128(sa);
+          const uint64_t db = umma_desc_kmajor_sw128(sa + Cfg::kStageBytesA);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advancing 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the 16-byte address field
+            umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full_bar[acc_stage]);  // accumulator complete
+        if (++acc_stage == 2) {
+          acc_stage = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===== epilogue warps (2..5): TMEM lane group = warp % 4 =====
+    const int lg = warp & 3;
+    const int row_in_tile = lg * 32 + lane;
+    int acc_stage = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
+      const TileCoord c = tile_coord(t, g);
+      mbar_wait(&tmem_full_bar[acc_stage], acc_phase);
+      tcgen05_fence_after();
+      const int r = c.m_blk * BLOCK_M + row_in_tile;  // row within the batch
+      const bool row_ok = r < p.rows_valid;
+      const long orow = (long)c.batch * p.out_batch_pitch + (long)(r + p.out_row_offset) * p.ldo;
+      float best = -FLT_MAX;
+      int best_idx = 0x7fffffff;
+#pragma unroll 1
+      for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + acc_stage * BLOCK_N + ch * 32;
+        tmem_ld_32x32b_x32(taddr, v);
+        tcgen05_wait_ld();
+        const int n0 = c.n_blk * BLOCK_N + ch * 32;
+        if (!row_ok || n0 >= p.N) continue;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (n0 + j < p.N) {
+              const float4 bv = *reinterpret_cast<const float4*>(p.bias + n0 + j);
+              f[j] += bv.x, f[j + 1] += bv.y, f[j + 2] += bv.z, f[j + 3] += bv.w;
+            }
+          }
+        }
+        const bool full = n0 + 32 <= p.N;
+        if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
+          if constexpr (EPI == EPI_BIAS_GELU_BF16) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+          }
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + orow + n0;
+          if (full) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 u;
+              u.x = pack_bf16x2(f[j], f[j + 1]), u.y = pack_bf16x2(f[j + 2], f[j + 3]);
+              u.z = pack_bf16x2(f[j + 4], f[j + 5]), u.w = pack_bf16x2(f[j + 6], f[j + 7]);
+              *reinterpret_cast<uint4*>(o + j) = u;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.N) o[j] = __float2bfloat16_rn(f[j]);
+          }
+        } else if constexpr (EPI == EPI_BIAS_F32 || EPI == EPI_BIAS_RESID_F32 || EPI == EPI_GELU_POS_F32) {
+          float* o = reinterpret_cast<float*>(p.out) + orow + n0;
+          if constexpr (EPI == EPI_GELU_POS_F32) {
+            const float* pe = p.pos + (long)r * p.N + n0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (n0 + j < p.N) {
+                const float4 pv = *reinterpret_cast<const float4*>(pe + j);
+                f[j] = gelu_erf(f[j]) + pv.x, f[j + 1] = gelu_erf(f[j + 1]) + pv.y;
+                f[j + 2] = gelu_erf(f[j + 2]) + pv.z, f[j + 3] = gelu_erf(f[j + 3]) + pv.w;
+              }
+            }
+          }
+          if (full) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 u = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+              if constexpr (EPI == EPI_BIAS_RESID_F32) {
+                const float4 rv = *reinterpret_cast<const float4*>(o + j);
+                u.x += rv.x, u.y += rv.y, u.z += rv.z, u.w += rv.w;
+              }
+              *reinterpret_cast<float4*>(o + j) = u;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.N) o[j] = (EPI == EPI_BIAS_RESID_F32 ? o[j] : 0.f) + f[j];
+          }
+        } else if constexpr (EPI == EPI_CROSSKV_BF16) {
+          // n0 is 32-aligned, so the chunk stays inside one (layer, k|v, head) slice of 64 columns
+          const int which = n0 / p.d_model;          // layer * 2 + kv
+          const int within = n0 - which * p.d_model;
+          const int h = within >> 6, dh = within & 63;
+          const int layer = which >> 1;
+          __nv_bfloat16* base = (which & 1) ? p.cross_v : p.cross_k;
+          const long off = ((((long)layer * p.kv_batch + (c.batch + p.kv_batch_offset)) * p.n_head + h) * p.n_ctx_kv + r) * 64 + dh;
+          __nv_bfloat16* o = base + off;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 u;
+            u.x = pack_bf16x2(f[j], f[j + 1]), u.y = pack_bf16x2(f[j + 2], f[j + 3]);
+            u.z = pack_bf16x2(f[j + 4], f[j + 5]), u.w = pack_bf16x2(f[j + 6], f[j + 7]);
+            *reinterpret_cast<uint4*>(o + j) = u;
+          }
+        } else if constexpr (EPI == EPI_ARGMAX) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (n0 + j < p.N && f[j] > best) {  // strict '>' keeps the first maximum (std::max_element, Whisper.cpp:42-45)
+              best = f[j];
+              best_idx = n0 + j;
+            }
+          }
+          if (p.out != nullptr) {
+            float* o = reinterpret_cast<float*>(p.out) + orow + n0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.N) o[j] = f[j];
+          }
+        }
+      }
+      if constexpr (EPI == EPI_ARGMAX) {
+        if (row_ok) {
+          const long pi = ((long)c.batch * p.rows_valid + r) * p.part_ld + c.n_blk;
+          p.part_val[pi] = best;
+          p.part_idx[pi] = best_idx;
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc_stage]);
+      if (++acc_stage == 2) {
+        acc_stage = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || p == nullptr) throw CudaError("cuTensorMapEncodeTiled not available from the driver");
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+CUtensorMap make_tmap(const void* base, int rank, const uint64_t* dims, const uint64_t* pitches_bytes, const uint32_t* box) {
+  CUtensorMap m;
+  cuuint64_t gdim[3], gstr[2];
+  cuuint32_t bdim[3], estr[3];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+  }
+  for (int i = 0; i < rank - 1; ++i) gstr[i] = pitches_bytes[i];
+  CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu)", (int)r, rank,
+             (unsigned long long)dims[0], (unsigned long long)dims[1]);
+    throw CudaError(buf);
+  }
+  return m;
+}
+
+template <int BLOCK_N, int EPI>
+void launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmGeom& g, const GemmParams& p, int grid, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  gemm_tcgen05_kernel<BLOCK_N, EPI><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, g, p);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+template <int EPI>
+void launch_bn(int block_n, const CUtensorMap& ta, const CUtensorMap& tb, const GemmGeom& g, const GemmParams& p, int grid,
+               cudaStream_t stream) {
+  switch (block_n) {
+    case 256: launch_one<256, EPI>(ta, tb, g, p, grid, stream); break;
+    case 128: launch_one<128, EPI>(ta, tb, g, p, grid, stream); break;
+    case 64: launch_one<64, EPI>(ta, tb, g, p, grid, stream); break;
+    case 32: launch_one<32, EPI>(ta, tb, g, p, grid, stream); break;
+    default: throw CudaError("gemm: unsupported BLOCK_N");
+  }
+}
+
+template <int BLOCK_N, int EPI>
+void set_attr_one() {
+  CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BLOCK_N>::kSmemBytes));
+}
+template <int EPI>
+void set_attr_epi() {
+  set_attr_one<256, EPI>();
+  set_attr_one<128, EPI>();
+  set_attr_one<64, EPI>();
+  set_attr_one<32, EPI>();
+}
+
+}  // namespace
+
+void gemm_set_attributes() {
+  set_attr_epi<EPI_BIAS_BF16>();
+  set_attr_epi<EPI_BIAS_GELU_BF16>();
+  set_attr_epi<EPI_BIAS_F32>();
+  set_attr_epi<EPI_BIAS_RESID_F32>();
+  set_attr_epi<EPI_GELU_POS_F32>();
+  set_attr_epi<EPI_CROSSKV_BF16>();
+  set_attr_epi<EPI_ARGMAX>();
+}
+
+struct GemmPlan {
+  CUtensorMap tmap_a, tmap_b;
+  GemmGeom geom;
+  int block_n, epilogue, grid;
+};
+
+GemmPlan* gemm_plan_create(const GemmOperandA& a, const __nv_bfloat16* w, int n_rows_w, int block_n, int epilogue) {
+  if ((a.row_pitch * 2) % 16 != 0 || (a.batch_pitch * 2) % 16 != 0) throw CudaError("gemm: operand pitches must be multiples of 16 bytes");
+  GemmPlan* pl = new GemmPlan();
+  const uint64_t adims[3] = {(uint64_t)a.K, (uint64_t)a.rows, (uint64_t)a.n_batch};
+  const uint64_t apitch[2] = {(uint64_t)a.row_pitch * 2, (uint64_t)(a.n_batch > 1 ? a.batch_pitch : (long)a.rows * a.row_pitch) * 2};
+  const uint32_t abox[3] = {BLOCK_K, BLOCK_M, 1};
+  pl->tmap_a = make_tmap(a.ptr, 3, adims, apitch, abox);
+  const int n_taps = a.n_taps > 0 ? a.n_taps : 1;
+  const int k_per_tap = a.n_taps > 0 ? a.k_per_tap : a.K;
+  const long w_k = (long)n_taps * k_per_tap;  // W is [n_rows_w][n_taps * k_per_tap], row-major
+  if ((w_k * 2) % 16 != 0) throw CudaError("gemm: weight row pitch must be a multiple of 16 bytes");
+  const uint64_t bdims[2] = {(uint64_t)w_k, (uint64_t)n_rows_w};
+  const uint64_t bpitch[1] = {(uint64_t)w_k * 2};
+  const uint32_t bbox[2] = {BLOCK_K, (uint32_t)block_n};
+  pl->tmap_b = make_tmap(w, 2, bdims, bpitch, bbox);
+  pl->block_n = block_n;
+  pl->epilogue = epilogue;
+  pl->geom.n_batch = a.n_batch;
+  pl->geom.n_taps = n_taps;
+  pl->geom.kb_per_tap = (k_per_tap + BLOCK_K - 1) / BLOCK_K;
+  pl->geom.num_k_blocks = n_taps * pl->geom.kb_per_tap;
+  for (int t = 0; t < 3; ++t) {
+    pl->geom.a_c0[t] = a.n_taps > 0 ? a.tap_c0[t] : 0;
+    pl->geom.a_row[t] = a.n_taps > 0 ? a.tap_row[t] : 0;
+    pl->geom.w_k0[t] = t * k_per_tap;
+  }
+  pl->geom.m_tiles_per_batch = 0;  // set at launch (depends on rows_valid)
+  pl->geom.n_tiles = 0;
+  return pl;
+}
+
+void gemm_plan_destroy(GemmPlan* p) { delete p; }
+
+void gemm_launch(const GemmPlan* plan, const GemmParams& p, cudaStream_t stream) {
+  GemmGeom g = plan->geom;
+  g.m_tiles_per_batch = (p.rows_valid + BLOCK_M - 1) / BLOCK_M;
+  g.n_tiles = (p.N + plan->block_n - 1) / plan->block_n;
+  if (p.n_batch > 0) g.n_batch = p.n_batch;
+  g.total_tiles = g.n_batch * g.m_tiles_per_batch * g.n_tiles;
+  if (g.total_tiles <= 0) return;
+  const int grid = g.total_tiles < kNumSMs ? g.total_tiles : kNumSMs;
+  switch (plan->epilogue) {
+    case EPI_BIAS_BF16: launch_bn<EPI_BIAS_BF16>(plan->block_n, plan->tmap_a, plan->tmap_b, g, p, grid, stream); break;
+    case EPI_BIAS_GELU_BF16: launch_bn<EPI_BIAS_GELU_BF16>(plan->block_n, plan->tmap_a, plan->tmap_b, g, p, grid, stream); break;
+    case EPI_BIAS_F32: launch_bn<EPI_BIAS_F32>(plan->block_n, plan->tmap_a, plan->tmap_b, g, p, grid, stream); break;
+    case EPI_BIAS_RESID_F32: launch_bn<EPI_BIAS_RESID_F32>(plan->block_n, plan->tmap_a, plan->tmap_b, g, p, grid, stream); break;
+    case EPI_GELU_POS_F32: launch_bn<EPI_GELU_POS_F32>(plan->block_n, plan->tmap_a, plan->tmap_b, g, p, grid, stream); break;
+    case EPI_CROSSKV_BF16: launch_bn<EPI_CROSSKV_BF16>(plan->block_n, plan->tmap_a, plan->tmap_b, g, p, grid, stream); break;
+    case EPI_ARGMAX: launch_bn<EPI_ARGMAX>(plan->block_n, plan->tmap_a, plan->tmap_b, g, p, grid, stream); break;
+    default: throw CudaError("gemm: unknown epilogue");
+  }
+}
+
+// ---- SIMT comparator (self-tests only) ------------------------------------------------------------------
+namespace {
+__global__ void gemm_reference_simt_kernel(const __nv_bfloat16* __restrict__ a, long lda, const __nv_bfloat16* __restrict__ w, long ldw,
+                                           const float* __restrict__ bias, float* __restrict__ out, long ldo, int M, int N, int K) {
+  __shared__ float sa[16][17], sw[16][17];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int m = blockIdx.y * 16 + ty, n = blockIdx.x * 16 + tx;
+  float acc = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    const int am = blockIdx.y * 16 + ty, wn = blockIdx.x * 16 + ty;
+    sa[ty][tx] = (am < M && k0 + tx < K) ? __bfloat162float(a[am * lda + k0 + tx]) : 0.f;
+    sw[ty][tx] = (wn < N && k0 + tx < K) ? __bfloat162float(w[wn * ldw + k0 + tx]) : 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc = fmaf(sa[ty][k], sw[tx][k], acc);
+    __syncthreads();
+  }
+  if (m < M && n < N) out[m * ldo + n] = acc + (bias ? bias[n] : 0.f);
+}
+}  // namespace
+
+void gemm_reference_simt(const __nv_bfloat16* a, long lda, const __nv_bfloat16* w, long ldw, const float* bias, float* out, long ldo,
+                         int M, int N, int K, cudaStream_t stream) {
+  dim3 grid((N + 15) / 16, (M + 15) / 16), block(16, 16);
+  gemm_reference_simt_kernel<<<grid, block, 0, stream>>>(a, lda, w, ldw, bias, out, ldo, M, N, K);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace b200w
