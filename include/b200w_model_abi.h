@@ -84,7 +84,8 @@ B200W_API int b200w_transcribe_resident(b200w_engine* e, int B, const char* lang
                                         int max_tokens, int* n_tokens_out, b200w_times* times);
 
 /* Stage runners on resident data without host traffic (benchmarks / profiling): each enqueues on the engine stream and
- * returns the CUDA-event time of `iters` back-to-back runs in *ms. stage: 0 = log-mel, 1 = encoder, 2 = decode (n_steps). */
+ * returns the CUDA-event time of `iters` back-to-back runs in *ms. stage: 0 = log-mel, 1 = encoder, 2 = decode (n_steps),
+ * 3 = only the cross-attention decode kernel, one launch per decoder layer. */
 B200W_API int b200w_time_stage(b200w_engine* e, int stage, int B, int iters, int n_steps, float* ms);
 
 /* Test hooks: tcgen05 GEMM against the SIMT comparator on random data (returns max abs difference), constant tables. */

@@ -33,7 +33,7 @@ def test_teacher_forced_logits(setup):
     ref_logits = np.stack(ref["logits"])  # [n, B, V]
     err = np.abs(logits[:n] - ref_logits).max()
     print("teacher-forced logits max-abs err %.4f (max |logit| %.2f)" % (err, np.abs(ref_logits).max()))
-    assert err <= util.LOGIT_TOL
+    assert err <= util.logit_tol(ref_logits)
     margins = np.stack(ref["top2_margin"])
     bad = 0
     for i in range(n):
@@ -47,9 +47,13 @@ def test_teacher_forced_logits(setup):
 def test_free_running_tokens(setup):
     eng, oracle, ck, cv, B = setup
     n = 32
-    ref = oracle.greedy(ck, cv, max_new_tokens=n, honor_eot=False)
+    ref = oracle.greedy(ck, cv, max_new_tokens=n, honor_eot=False, keep_logits=True)
     toks, _ = eng.greedy(B, max_new_tokens=n, honor_eot=False)
-    assert util.tokens_agree(toks, ref["tokens"], ref["top2_margin"], util.LOGIT_TOL), (toks, ref["tokens"])
+    # a flip needs both logits to move towards each other: margin threshold = 2 x the logit tolerance
+    tol = 2 * util.logit_tol(np.stack(ref["logits"]))
+    assert util.tokens_agree(toks, ref["tokens"], ref["top2_margin"], tol), (toks, ref["tokens"])
+    same = sum(a == b for x, y in zip(toks, ref["tokens"]) for a, b in zip(x, y))
+    print("free-running: %d of %d tokens identical to the oracle" % (same, n * B))
     # CUDA-graph path and eager path are the same kernels: identical output
     toks2, _ = eng.greedy(B, max_new_tokens=n, honor_eot=False, keep_logits=True)
     assert toks == toks2
@@ -73,19 +77,19 @@ def test_model_abi_steps(setup):
             self_k[:, :, i], self_v[:, :, i] = rk, rv
             assert np.abs(k4[:, :, i] - rk.numpy()).max() <= 2e-2 * max(1.0, float(rk.abs().max()))
             assert np.abs(v4[:, :, i] - rv.numpy()).max() <= 2e-2 * max(1.0, float(rv.abs().max()))
-        assert np.abs(logits - rl.numpy()).max() <= util.LOGIT_TOL
+        assert np.abs(logits - rl.numpy()).max() <= util.logit_tol(rl.numpy())
         nxt = rl.argmax(-1)
         mask[3] = 0
         rl2, rk2, _ = oracle.decoder_step(nxt, self_k, self_v, ck, cv, 4, mask)
     l2, k1, _ = eng.decoder_loop(nxt.numpy().astype(np.int32), 4)
-    assert np.abs(l2 - rl2.numpy()).max() <= util.LOGIT_TOL
+    assert np.abs(l2 - rl2.numpy()).max() <= util.logit_tol(rl2.numpy())
     assert np.abs(k1 - rk2.numpy()).max() <= 2e-2 * max(1.0, float(rk2.abs().max()))
 
 
 def test_eot_is_honoured(setup):
     eng, oracle, ck, cv, B = setup
-    ref = oracle.greedy(ck, cv, max_new_tokens=40, honor_eot=True)
+    ref = oracle.greedy(ck, cv, max_new_tokens=40, honor_eot=True, keep_logits=True)
     toks, _ = eng.greedy(B, max_new_tokens=40, honor_eot=True)
     eot = int(oracle.cfg["eot"])
     assert all(eot not in t for t in toks)
-    assert util.tokens_agree(toks, ref["tokens"], ref["top2_margin"], util.LOGIT_TOL)
+    assert util.tokens_agree(toks, ref["tokens"], ref["top2_margin"], 2 * util.logit_tol(np.stack(ref["logits"])))

@@ -528,6 +528,17 @@ void Engine::enqueue_decode_step(int B, bool want_logits) {
   launches_ += 2;
 }
 
+void Engine::run_cross_attention_only(int B) {
+  const int H = cfg_.n_head;
+  const int n_split = cross_attention_pick_split(B, H);
+  for (int l = 0; l < cfg_.l_dec; ++l) {
+    const size_t ckv_off = (size_t)l * cap_ * H * kAudioCtx * 64;
+    launch_cross_attention_decode(q_dec_, cross_k_ + ckv_off, cross_v_ + ckv_off, attn_dec_, B, H, kAudioCtx, n_split, part_m_, part_l_,
+                                  part_o_, stream_);
+    launches_ += 1 + (n_split > 1 ? 1 : 0);
+  }
+}
+
 void Engine::decode_reset(int B) {
   CUDA_CHECK(cudaMemsetAsync(st_.step, 0, sizeof(int), stream_));
   CUDA_CHECK(cudaMemsetAsync(st_.finished, 0, sizeof(int) * B, stream_));

@@ -100,6 +100,9 @@ class Engine {
   void transcribe_resident(int B, int max_samples, const std::string& lang, const DecodeOptions& opt,
                            std::vector<std::vector<int>>* tokens, StageTimes* times);
 
+  // profiling helper: only the cross-attention decode kernel, once per decoder layer, on the resident K/V
+  void run_cross_attention_only(int B);
+
   long launches() const { return launches_; }
 
  private:

@@ -229,6 +229,8 @@ int b200w_time_stage(b200w_engine* e, int stage, int B, int iters, int n_steps, 
         o.honor_eot = false;
         o.max_new_tokens = std::max(1, std::min(n_steps, kTextCtx) - kSotLen);
         E.run_decode(B, E.sot_sequence("zh"), o, nullptr);
+      } else if (stage == 3) {
+        E.run_cross_attention_only(B);
       } else {
         throw std::runtime_error("time_stage: unknown stage");
       }
