@@ -36,6 +36,14 @@ CHUNK_S = 30.0
 CHUNK_SAMPLES = 480000
 
 
+def shard_range(n_items, rank, world):
+    """Static contiguous split of a list of independent utterances / 30 s windows across ranks:
+    rank r owns [lo, hi); sizes differ by at most one; concatenating the ranks' results in rank order restores the order."""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):

@@ -124,6 +124,37 @@ struct Engine::LayerDec {
 // ---------------------------------------------------------------------------------------------------------
 // construction / loading
 // ---------------------------------------------------------------------------------------------------------
+ModelConfig load_model_config(const std::string& model_root, const std::string& model_type) {
+  ModelConfig c;
+  const std::string cfg_path = model_root + "/" + model_type + "/" + model_type + "_config.json";
+  std::ifstream cf(cfg_path);
+  if (!cf) throw std::runtime_error("Cannot open config file: " + cfg_path);
+  std::stringstream ss;
+  ss << cf.rdbuf();
+  const JsonFlat j = parse_flat_json(ss.str());
+  c.n_mels = j.get_int("n_mels");
+  c.n_vocab = j.get_int("n_vocab");
+  c.d = j.get_int("n_text_state");
+  c.n_text_ctx = j.get_int("n_text_ctx");
+  c.l_dec = j.get_int("n_text_layer");
+  c.l_enc = j.get_int("n_audio_layer");
+  c.n_head = j.get_int("n_text_head");
+  c.n_audio_ctx = j.has("n_audio_ctx") ? j.get_int("n_audio_ctx") : kAudioCtx;
+  c.sot = j.get_int("sot");
+  c.eot = j.get_int("eot");
+  c.transcribe = j.get_int("transcribe");
+  c.no_timestamps = j.get_int("no_timestamps");
+  for (const std::string& t : split_csv(j.get_str("all_language_tokens"))) c.lang_tokens.push_back(std::stoi(t));
+  c.lang_codes = split_csv(j.get_str("all_language_codes"));
+  if (c.lang_tokens.size() != c.lang_codes.size()) throw std::runtime_error("config: language token / code lists differ in length");
+  if (j.get_int("n_audio_state") != c.d || j.get_int("n_audio_head") != c.n_head)
+    throw std::runtime_error("config: encoder and decoder widths differ (unsupported)");
+  if (c.d != c.n_head * 64) throw std::runtime_error("config: head_dim must be 64");
+  if (c.n_text_ctx != kTextCtx || c.n_audio_ctx != kAudioCtx) throw std::runtime_error("config: unexpected context sizes");
+  if (c.n_mels != 80 && c.n_mels != 128) throw std::runtime_error("config: n_mels must be 80 or 128");
+  return c;
+}
+
 Engine::Engine(const std::string& model_root, const std::string& model_type, int device, int max_batch) : device_(device) {
   int n_dev = 0;
   cudaError_t e = cudaGetDeviceCount(&n_dev);
@@ -137,34 +168,8 @@ Engine::Engine(const std::string& model_root, const std::string& model_type, int
   CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
   CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&pinned_flags_), 4096 * sizeof(int)));
 
-  // directory convention of the reference: {root}/{type}/{type}-*.{...}   (Whisper.cpp:87-90)
-  const std::string dir = model_root + "/" + model_type;
-  const std::string cfg_path = dir + "/" + model_type + "_config.json";
-  std::ifstream cf(cfg_path);
-  if (!cf) throw std::runtime_error("Cannot open config file: " + cfg_path);
-  std::stringstream ss;
-  ss << cf.rdbuf();
-  const JsonFlat j = parse_flat_json(ss.str());
-  cfg_.n_mels = j.get_int("n_mels");
-  cfg_.n_vocab = j.get_int("n_vocab");
-  cfg_.d = j.get_int("n_text_state");
-  cfg_.n_text_ctx = j.get_int("n_text_ctx");
-  cfg_.l_dec = j.get_int("n_text_layer");
-  cfg_.l_enc = j.get_int("n_audio_layer");
-  cfg_.n_head = j.get_int("n_text_head");
-  cfg_.n_audio_ctx = j.has("n_audio_ctx") ? j.get_int("n_audio_ctx") : kAudioCtx;
-  cfg_.sot = j.get_int("sot");
-  cfg_.eot = j.get_int("eot");
-  cfg_.transcribe = j.get_int("transcribe");
-  cfg_.no_timestamps = j.get_int("no_timestamps");
-  for (const std::string& t : split_csv(j.get_str("all_language_tokens"))) cfg_.lang_tokens.push_back(std::stoi(t));
-  cfg_.lang_codes = split_csv(j.get_str("all_language_codes"));
-  if (cfg_.lang_tokens.size() != cfg_.lang_codes.size()) throw std::runtime_error("config: language token / code lists differ in length");
-  if (j.get_int("n_audio_state") != cfg_.d || j.get_int("n_audio_head") != cfg_.n_head)
-    throw std::runtime_error("config: encoder and decoder widths differ (unsupported)");
-  if (cfg_.d != cfg_.n_head * 64) throw std::runtime_error("config: head_dim must be 64");
-  if (cfg_.n_text_ctx != kTextCtx || cfg_.n_audio_ctx != kAudioCtx) throw std::runtime_error("config: unexpected context sizes");
-  if (cfg_.n_mels != 80 && cfg_.n_mels != 128) throw std::runtime_error("config: n_mels must be 80 or 128");
+  const std::string dir = model_root + "/" + model_type;  // {root}/{type}/{type}-*  (Whisper.cpp:87-90)
+  cfg_ = load_model_config(model_root, model_type);
 
   logmel_upload_tables();
   kernels_set_attributes();
@@ -175,8 +180,7 @@ Engine::Engine(const std::string& model_root, const std::string& model_type, int
 Engine::~Engine() {
   cudaSetDevice(device_);
   cudaStreamSynchronize(stream_);
-  for (auto& kv : graphs_) cudaGraphExecDestroy(kv.second);
-  free_workspace();
+  free_workspace();  // also destroys the captured decode graphs
   for (void* p : owned_) cudaFree(p);
   if (pinned_flags_) cudaFreeHost(pinned_flags_);
   if (stream_) cudaStreamDestroy(stream_);

@@ -29,6 +29,9 @@ struct ModelConfig {              // the keys Whisper::load_models reads (Whispe
   std::vector<std::string> lang_codes;
 };
 
+// parses {root}/{type}/{type}_config.json (keys of /root/reference/model_convert/export_onnx.py:592-625) and validates it
+ModelConfig load_model_config(const std::string& model_root, const std::string& model_type);
+
 struct HostTensor {
   std::vector<size_t> dims;
   const float* data = nullptr;  // points into the mmapped / loaded file image

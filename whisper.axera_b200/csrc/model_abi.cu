@@ -8,6 +8,7 @@
 
 #include "common.cuh"
 #include "engine.h"
+#include "host_utils.h"
 
 using namespace b200w;
 
@@ -241,6 +242,40 @@ int b200w_time_stage(b200w_engine* e, int stage, int B, int iters, int n_steps, 
     cudaEventDestroy(a);
     cudaEventDestroy(b);
   });
+}
+
+// ---- host-logic test hooks (no GPU needed) ----
+int b200w_test_parse_config(const char* model_path, const char* model_type, b200w_dims* out, int* n_languages) {
+  if (!model_path || !model_type || !out) return -1;
+  return guarded([&] {
+    const ModelConfig c = load_model_config(model_path, model_type);
+    out->n_mels = c.n_mels, out->n_vocab = c.n_vocab, out->d_model = c.d, out->n_head = c.n_head;
+    out->n_audio_layer = c.l_enc, out->n_text_layer = c.l_dec, out->n_audio_ctx = c.n_audio_ctx, out->n_text_ctx = c.n_text_ctx;
+    out->sot = c.sot, out->eot = c.eot, out->transcribe = c.transcribe, out->no_timestamps = c.no_timestamps;
+    if (n_languages) *n_languages = (int)c.lang_codes.size();
+  });
+}
+int b200w_test_load_wav(const char* path, float* out, int capacity_frames, int* n_frames, int* n_channels, int* sample_rate) {
+  if (!path || !n_frames || !n_channels || !sample_rate) return -1;
+  return guarded([&] {
+    WavData w;
+    std::string err;
+    if (!load_wav(path, &w, &err)) throw std::runtime_error(err);
+    *n_channels = (int)w.channels.size();
+    *n_frames = (int)w.channels[0].size();
+    *sample_rate = w.sample_rate;
+    // channel-interleaved copy [frame][channel]
+    if (out)
+      for (int i = 0; i < *n_frames && i < capacity_frames; ++i)
+        for (int c = 0; c < *n_channels; ++c) out[(size_t)i * *n_channels + c] = w.channels[c][i];
+  });
+}
+int b200w_test_base64(const char* in, unsigned char* out, int capacity) {
+  if (!in || !out) return -1;
+  const std::string s = base64_decode(in);
+  const int n = (int)s.size() < capacity ? (int)s.size() : capacity;
+  memcpy(out, s.data(), n);
+  return (int)s.size();
 }
 
 int b200w_mel_tables(int n_mels, float* bank, float* window) {
