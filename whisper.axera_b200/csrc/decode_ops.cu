@@ -11,6 +11,7 @@
 // K/V live in HBM as bf16, head-major [B][H][n][64]: one (sequence, head) is a contiguous 128-byte-per-key stream,
 // read with 16-byte loads (8 lanes per key, 4 keys per warp instruction), fp32 scores / softmax / accumulation.
 #include <cfloat>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -164,6 +165,8 @@ __device__ __forceinline__ void attend_one_query(const float* __restrict__ q_glo
 // ---- embedding -------------------------------------------------------------------------------------------
 __global__ void embed_kernel(const int* __restrict__ step_ptr, const int* __restrict__ tokens, const float* __restrict__ tok_emb,
                              const float* __restrict__ pos_emb, float* __restrict__ x, int d, int n_text_ctx) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int b = blockIdx.x;
   const int step = *step_ptr;
   const int tok = tokens[(long)b * n_text_ctx + step];
@@ -177,34 +180,103 @@ __global__ void embed_kernel(const int* __restrict__ step_ptr, const int* __rest
 }
 
 // ---- self attention ----------------------------------------------------------------------------------------
-constexpr int kSelfThreads = 128;
-__global__ void __launch_bounds__(kSelfThreads) self_attention_decode_kernel(const float* __restrict__ qkv, __nv_bfloat16* __restrict__ k_cache,
-                                                                            __nv_bfloat16* __restrict__ v_cache, const int* __restrict__ step_ptr,
-                                                                            __nv_bfloat16* __restrict__ out, int n_head, int n_ctx) {
-  __shared__ float s_scores[512];
-  __shared__ float s_red[kSelfThreads / 32];
-  __shared__ float s_out[64];
-  __shared__ float s_ml[2];
-  __shared__ float s_k1[64], s_v1[64];
-  const int h = blockIdx.x, b = blockIdx.y;
+// One warp per (sequence, head): the cache of a head is at most 447 keys, so a whole CTA with block-wide reductions is
+// all latency.  8 lanes share a key (16 bytes each), 4 keys per warp instruction; every key slot runs its own online
+// softmax (max, sum, 8-wide accumulator per lane) and the four slots plus the current token (fp32 k1/v1) are merged
+// with shuffles at the end.  No shared memory, no block barrier.
+constexpr int kSelfWarps = 4;
+__global__ void __launch_bounds__(kSelfWarps * 32) self_attention_decode_kernel(const float* __restrict__ qkv, __nv_bfloat16* __restrict__ k_cache,
+                                                                               __nv_bfloat16* __restrict__ v_cache, const int* __restrict__ step_ptr,
+                                                                               __nv_bfloat16* __restrict__ out, int n_pairs, int n_head, int n_ctx) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int pair = blockIdx.x * kSelfWarps + (threadIdx.x >> 5);  // b * n_head + h
+  if (pair >= n_pairs) return;
+  const int lane = threadIdx.x & 31, grp = lane >> 3, sub = lane & 7;
+  const int b = pair / n_head, h = pair - b * n_head;
   const int d = n_head * 64;
   const int pos = *step_ptr;  // cached positions 0..pos-1, current token at pos
-  const float* q = qkv + (long)b * 3 * d + h * 64;
-  const float* k1 = q + d;
-  const float* v1 = q + 2 * d;
-  __nv_bfloat16* Kc = k_cache + ((long)b * n_head + h) * n_ctx * 64;
-  __nv_bfloat16* Vc = v_cache + ((long)b * n_head + h) * n_ctx * 64;
-  if (threadIdx.x < 64) {
-    s_k1[threadIdx.x] = k1[threadIdx.x];
-    s_v1[threadIdx.x] = v1[threadIdx.x];
+  const float* qg = qkv + (long)b * 3 * d + h * 64 + sub * 8;
+  __nv_bfloat16* Kc = k_cache + (long)pair * n_ctx * 64;
+  __nv_bfloat16* Vc = v_cache + (long)pair * n_ctx * 64;
+  float q[8], k1[8], v1[8];
+  {
+    const float4 a = *reinterpret_cast<const float4*>(qg), c = *reinterpret_cast<const float4*>(qg + 4);
+    q[0] = a.x, q[1] = a.y, q[2] = a.z, q[3] = a.w, q[4] = c.x, q[5] = c.y, q[6] = c.z, q[7] = c.w;
+    const float4 ka = *reinterpret_cast<const float4*>(qg + d), kb = *reinterpret_cast<const float4*>(qg + d + 4);
+    k1[0] = ka.x, k1[1] = ka.y, k1[2] = ka.z, k1[3] = ka.w, k1[4] = kb.x, k1[5] = kb.y, k1[6] = kb.z, k1[7] = kb.w;
+    const float4 va = *reinterpret_cast<const float4*>(qg + 2 * d), vb = *reinterpret_cast<const float4*>(qg + 2 * d + 4);
+    v1[0] = va.x, v1[1] = va.y, v1[2] = va.z, v1[3] = va.w, v1[4] = vb.x, v1[5] = vb.y, v1[6] = vb.z, v1[7] = vb.w;
   }
-  __syncthreads();
-  attend_one_query<kSelfThreads>(q, Kc, Vc, 0, pos, s_k1, s_v1, s_scores, s_red, s_out, s_ml);
-  if (threadIdx.x < 64) {
-    out[(long)b * d + h * 64 + threadIdx.x] = __float2bfloat16_rn(s_out[threadIdx.x] / s_ml[1]);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) q[i] *= kScoreScaleLog2;
+  float m = -INFINITY, l = 0.f, acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  constexpr int U = 4;
+  for (int jb = 0; jb < pos; jb += 4 * U) {  // warp-uniform bounds
+    uint4 kk[U], vv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int j = jb + u * 4 + grp;
+      const bool ok = j < pos;
+      kk[u] = ok ? ld_stream16(Kc + (long)j * 64 + sub * 8) : make_uint4(0, 0, 0, 0);
+      vv[u] = ok ? ld_stream16(Vc + (long)j * 64 + sub * 8) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int j = jb + u * 4 + grp;
+      float sc = dot8(kk[u], q);
+      sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+      sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+      sc += __shfl_xor_sync(0xffffffffu, sc, 4);
+      if (j < pos) {
+        const float m_new = fmaxf(m, sc);
+        const float corr = exp2f(m - m_new), pw = exp2f(sc - m_new);
+        l = fmaf(l, corr, pw);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] *= corr;
+        axpy8(acc, pw, vv[u]);
+        m = m_new;
+      }
+    }
+  }
+  // current token (fp32): its score, then merge the four key slots and the current token
+  float s_cur = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s_cur = fmaf(q[i], k1[i], s_cur);
+  s_cur += __shfl_xor_sync(0xffffffffu, s_cur, 1);
+  s_cur += __shfl_xor_sync(0xffffffffu, s_cur, 2);
+  s_cur += __shfl_xor_sync(0xffffffffu, s_cur, 4);
+  float m_tot = fmaxf(m, s_cur);
+  m_tot = fmaxf(m_tot, __shfl_xor_sync(0xffffffffu, m_tot, 8));
+  m_tot = fmaxf(m_tot, __shfl_xor_sync(0xffffffffu, m_tot, 16));
+  const float corr = exp2f(m - m_tot);  // exp2(-inf) = 0 for an empty slot
+  l *= corr;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] *= corr;
+  l += __shfl_xor_sync(0xffffffffu, l, 8);
+  l += __shfl_xor_sync(0xffffffffu, l, 16);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
+    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+  }
+  const float pc = exp2f(s_cur - m_tot);
+  l += pc;
+  if (grp == 0) {
+    const float inv = 1.f / l;
+    uint4 o, kq, vq;
+    o.x = pack_bf16x2(fmaf(pc, v1[0], acc[0]) * inv, fmaf(pc, v1[1], acc[1]) * inv);
+    o.y = pack_bf16x2(fmaf(pc, v1[2], acc[2]) * inv, fmaf(pc, v1[3], acc[3]) * inv);
+    o.z = pack_bf16x2(fmaf(pc, v1[4], acc[4]) * inv, fmaf(pc, v1[5], acc[5]) * inv);
+    o.w = pack_bf16x2(fmaf(pc, v1[6], acc[6]) * inv, fmaf(pc, v1[7], acc[7]) * inv);
+    *reinterpret_cast<uint4*>(out + (long)b * d + h * 64 + sub * 8) = o;
     // append this token's key / value (the reference does this on the host after the step, Whisper.cpp:328-342)
-    Kc[(long)pos * 64 + threadIdx.x] = __float2bfloat16_rn(s_k1[threadIdx.x]);
-    Vc[(long)pos * 64 + threadIdx.x] = __float2bfloat16_rn(s_v1[threadIdx.x]);
+    kq.x = pack_bf16x2(k1[0], k1[1]), kq.y = pack_bf16x2(k1[2], k1[3]), kq.z = pack_bf16x2(k1[4], k1[5]), kq.w = pack_bf16x2(k1[6], k1[7]);
+    vq.x = pack_bf16x2(v1[0], v1[1]), vq.y = pack_bf16x2(v1[2], v1[3]), vq.z = pack_bf16x2(v1[4], v1[5]), vq.w = pack_bf16x2(v1[6], v1[7]);
+    *reinterpret_cast<uint4*>(Kc + (long)pos * 64 + sub * 8) = kq;
+    *reinterpret_cast<uint4*>(Vc + (long)pos * 64 + sub * 8) = vq;
   }
 }
 
@@ -218,6 +290,7 @@ __global__ void __launch_bounds__(kCrossThreads) cross_attention_decode_kernel(c
   __shared__ float s_red[kCrossThreads / 32];
   __shared__ float s_out[64];
   __shared__ float s_ml[2];
+  pdl_wait();
   const int h = blockIdx.x / n_split, sp = blockIdx.x % n_split;
   const int b = blockIdx.y;
   const int d = n_head * 64;
@@ -226,6 +299,7 @@ __global__ void __launch_bounds__(kCrossThreads) cross_attention_decode_kernel(c
   const int k_begin = sp * per, k_end = min(T, k_begin + per);
   attend_one_query<kCrossThreads>(q + (long)b * d + h * 64, k + kv_off, v + kv_off, k_begin, k_end, nullptr, nullptr, s_scores, s_red,
                                   s_out, s_ml);
+  pdl_launch_dependents();  // multi-wave kernel: let the successor start only in this CTA's tail
   if (n_split == 1) {
     if (threadIdx.x < 64) out[(long)b * d + h * 64 + threadIdx.x] = __float2bfloat16_rn(s_out[threadIdx.x] / s_ml[1]);
   } else {
@@ -240,6 +314,8 @@ __global__ void __launch_bounds__(kCrossThreads) cross_attention_decode_kernel(c
 
 __global__ void cross_attention_combine_kernel(const float* __restrict__ part_m, const float* __restrict__ part_l,
                                                const float* __restrict__ part_o, __nv_bfloat16* __restrict__ out, int n_head, int n_split) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int h = blockIdx.x, b = blockIdx.y, t = threadIdx.x;  // 64 threads
   const long base = ((long)b * n_head + h) * n_split;
   float m = -INFINITY;
@@ -258,6 +334,8 @@ __global__ void __launch_bounds__(128) argmax_finalize_kernel(DecodeState st, co
                                                               int n_tiles, int part_ld, int n_text_ctx, int eot, int honor_eot, int sot_len) {
   __shared__ float s_v[4];
   __shared__ int s_i[4];
+  pdl_wait();
+  pdl_launch_dependents();
   const int b = blockIdx.x;
   float best = -FLT_MAX;
   int bi = 0x7fffffff;
@@ -287,21 +365,29 @@ __global__ void __launch_bounds__(128) argmax_finalize_kernel(DecodeState st, co
   }
 }
 
-__global__ void advance_step_kernel(int* step) { *step += 1; }
+__global__ void advance_step_kernel(int* step) {
+  pdl_wait();
+  pdl_launch_dependents();
+  *step += 1;
+}
 
 }  // namespace
 
+bool pdl_enabled() {
+  static const bool on = getenv("B200W_NO_PDL") == nullptr;
+  return on;
+}
+
 void launch_embed(const DecodeState& st, const float* tok_emb, const float* pos_emb, float* x, int B, int d, int n_text_ctx,
                   cudaStream_t stream) {
-  embed_kernel<<<B, 128, 0, stream>>>(st.step, st.tokens, tok_emb, pos_emb, x, d, n_text_ctx);
-  CUDA_CHECK(cudaGetLastError());
+  launch_pdl(embed_kernel, dim3(B), dim3(128), 0, stream, st.step, st.tokens, tok_emb, pos_emb, x, d, n_text_ctx);
 }
 
 void launch_self_attention_decode(const float* qkv, __nv_bfloat16* k_cache, __nv_bfloat16* v_cache, const int* step, __nv_bfloat16* out,
                                   int B, int n_head, int n_ctx, cudaStream_t stream) {
-  dim3 grid(n_head, B);
-  self_attention_decode_kernel<<<grid, kSelfThreads, 0, stream>>>(qkv, k_cache, v_cache, step, out, n_head, n_ctx);
-  CUDA_CHECK(cudaGetLastError());
+  const int n_pairs = B * n_head;
+  launch_pdl(self_attention_decode_kernel, dim3((n_pairs + kSelfWarps - 1) / kSelfWarps), dim3(kSelfWarps * 32), 0, stream, qkv, k_cache,
+             v_cache, step, out, n_pairs, n_head, n_ctx);
 }
 
 int cross_attention_pick_split(int B, int n_head) {
@@ -314,19 +400,14 @@ int cross_attention_pick_split(int B, int n_head) {
 void launch_cross_attention_decode(const float* q, const __nv_bfloat16* k, const __nv_bfloat16* v, __nv_bfloat16* out, int B, int n_head,
                                    int T, int n_split, float* part_m, float* part_l, float* part_o, cudaStream_t stream) {
   dim3 grid(n_head * n_split, B);
-  cross_attention_decode_kernel<<<grid, kCrossThreads, 0, stream>>>(q, k, v, out, n_head, T, n_split, part_m, part_l, part_o);
-  if (n_split > 1) {
-    dim3 g2(n_head, B);
-    cross_attention_combine_kernel<<<g2, 64, 0, stream>>>(part_m, part_l, part_o, out, n_head, n_split);
-  }
-  CUDA_CHECK(cudaGetLastError());
+  launch_pdl(cross_attention_decode_kernel, grid, dim3(kCrossThreads), 0, stream, q, k, v, out, n_head, T, n_split, part_m, part_l, part_o);
+  if (n_split > 1) launch_pdl(cross_attention_combine_kernel, dim3(n_head, B), dim3(64), 0, stream, part_m, part_l, part_o, out, n_head, n_split);
 }
 
 void launch_argmax_finalize(const DecodeState& st, const float* part_val, const int* part_idx, int n_tiles, int part_ld, int B,
                             int n_text_ctx, int eot, int honor_eot, int sot_len, cudaStream_t stream) {
-  argmax_finalize_kernel<<<B, 128, 0, stream>>>(st, part_val, part_idx, n_tiles, part_ld, n_text_ctx, eot, honor_eot, sot_len);
-  advance_step_kernel<<<1, 1, 0, stream>>>(st.step);
-  CUDA_CHECK(cudaGetLastError());
+  launch_pdl(argmax_finalize_kernel, dim3(B), dim3(128), 0, stream, st, part_val, part_idx, n_tiles, part_ld, n_text_ctx, eot, honor_eot, sot_len);
+  launch_pdl(advance_step_kernel, dim3(1), dim3(1), 0, stream, st.step);
 }
 
 }  // namespace b200w

@@ -19,6 +19,8 @@ constexpr int kLnMaxVec = 10;
 
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, int rows, int d) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -275,9 +277,15 @@ __global__ void __launch_bounds__(kAttThreads) encoder_attention_kernel(const __
 
 void launch_layernorm(const float* x, const float* gamma, const float* beta, __nv_bfloat16* y, int rows, int d, cudaStream_t stream) {
   if (d % 128 != 0 || d > 128 * kLnMaxVec) throw CudaError("layernorm: d must be a multiple of 128 and <= 1280");
-  const int warps_per_cta = 8;
-  layernorm_kernel<<<(rows + warps_per_cta - 1) / warps_per_cta, warps_per_cta * 32, 0, stream>>>(x, gamma, beta, y, rows, d);
-  CUDA_CHECK(cudaGetLastError());
+  // a decoder step normalises only B rows: spread them over more CTAs and let the launch overlap its predecessor (PDL)
+  const int warps_per_cta = rows <= 1024 ? 2 : 8;
+  const dim3 grid((rows + warps_per_cta - 1) / warps_per_cta), block(warps_per_cta * 32);
+  if (rows <= 1024) {
+    launch_pdl(layernorm_kernel, grid, block, 0, stream, x, gamma, beta, y, rows, d);
+  } else {
+    layernorm_kernel<<<grid, block, 0, stream>>>(x, gamma, beta, y, rows, d);
+    CUDA_CHECK(cudaGetLastError());
+  }
 }
 
 void encoder_ops_set_attributes() {

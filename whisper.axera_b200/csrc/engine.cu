@@ -364,7 +364,7 @@ void Engine::ensure_capacity(int B, long max_samples) {
   attn_dec_ = dev_alloc<__nv_bfloat16>(o, (size_t)dec_rows_pad_ * d);
   mlp_dec_ = dev_alloc<__nv_bfloat16>(o, (size_t)dec_rows_pad_ * 4 * d);
   logits_ = dev_alloc<float>(o, (size_t)cap_ * vocab_pad_);
-  logits_tiles_ = vocab_pad_ / 128;
+  logits_tiles_ = vocab_pad_ / 128 * 2;  // arg-max partials: two column halves per 128-wide logits tile (gemm epilogue)
   part_val_ = dev_alloc<float>(o, (size_t)cap_ * logits_tiles_);
   part_idx_ = dev_alloc<int>(o, (size_t)cap_ * logits_tiles_);
   const size_t np = (size_t)cap_ * H * 8;
@@ -503,7 +503,7 @@ void Engine::enqueue_decode_step(int B, bool want_logits) {
   GemmParams p{};
   auto gp = [&](void* out, long ldo, int N, const float* bias) {
     GemmParams q{};
-    q.rows_valid = B, q.N = N, q.out = out, q.ldo = ldo, q.bias = bias, q.n_batch = 1;
+    q.rows_valid = B, q.N = N, q.out = out, q.ldo = ldo, q.bias = bias, q.n_batch = 1, q.use_pdl = 1;
     return q;
   };
   for (int l = 0; l < cfg_.l_dec; ++l) {

@@ -7,12 +7,14 @@
 // time windows, attention / MLP projections of the encoder blocks :177-178, cross K/V projections :205-210,
 // every Linear of the decoder step :245-247,:228-230,:298 and the tied logits product :378-385).
 //
-// Structure (one CTA per SM, persistent over output tiles, 192 threads):
+// Structure (one CTA per SM, persistent over output tiles, 2 + 8 warps):
 //   warp 0  (1 lane)  TMA producer: A tile 128x64 and W tile BLOCK_Nx64 per k-block, SWIZZLE_128B, kStages ring
 //   warp 1  (1 lane)  MMA issuer: 4 x tcgen05.mma (M=128, N=BLOCK_N, K=16) per k-block into one of two TMEM
 //                     accumulator stages; tcgen05.commit releases smem slots / publishes the accumulator
-//   warps 2-5         epilogue: tcgen05.ld 32 columns at a time (thread = output row), fused bias / GELU /
-//                     residual / positional embedding / head-major scatter / arg-max, direct 16-byte stores
+//   warps 2-9         epilogue: tcgen05.ld 32 columns at a time (thread = output row; two warps per TMEM lane group
+//                     split the columns), software-pipelined against the next chunk's TMEM read and residual loads,
+//                     bias staged in smem; fused bias / GELU / residual / positional embedding / head-major scatter /
+//                     arg-max, direct 16-byte stores
 // Tile order is n-fastest so the CTAs in flight share A row-blocks and the whole W through L2.
 #include <cfloat>
 #include <mutex>
@@ -27,7 +29,6 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kGemmThreads = 192;
 constexpr int kSmemBudget = 196608;  // 192 KB of operand stages
 
 template <int BLOCK_N>
@@ -37,7 +38,9 @@ struct GemmCfg {
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
   static constexpr int kStages = kSmemBudget / kStageBytes;  // 256 -> 4, 128 -> 6, 64 -> 8, 32 -> 9
   static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kEpiWarps = BLOCK_N >= 64 ? 8 : 4;  // 8: two warps per TMEM lane group, each taking half of the columns
+  static constexpr int kThreads = 64 + 32 * kEpiWarps;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * BLOCK_N * 4 /*bias*/;
 };
 
 struct TileCoord {
@@ -62,7 +65,7 @@ __device__ __forceinline__ TileCoord tile_coord(int t, const GemmGeom& g) {
 }
 
 template <int BLOCK_N, int EPI>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(GemmCfg<BLOCK_N>::kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmGeom g,
                     const GemmParams p) {
   using Cfg = GemmCfg<BLOCK_N>;
@@ -88,7 +91,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty_bar[i], Cfg::kEpiWarps);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -100,6 +103,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  // everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap the previous kernel (PDL)
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -161,45 +167,71 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
     }
   } else {
-    // ===== epilogue warps (2..5): TMEM lane group = warp % 4 =====
+    // ===== epilogue warps: TMEM lane group = warp % 4; with 8 warps each lane group's columns are split in two halves =====
+    constexpr int kEpiWarps = Cfg::kEpiWarps;
+    constexpr int kEpiThreads = kEpiWarps * 32;
+    constexpr int CH_PER_WARP = (BLOCK_N / 32) / (kEpiWarps / 4);
+    constexpr bool kHasExtra = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_GELU_POS_F32);
     const int lg = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int etid = threadIdx.x - 64;
     const int row_in_tile = lg * 32 + lane;
+    float* s_bias = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + 256);  // [2][BLOCK_N]
     int acc_stage = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
       const TileCoord c = tile_coord(t, g);
-      mbar_wait(&tmem_full_bar[acc_stage], acc_phase);
-      tcgen05_fence_after();
       const int r = c.m_blk * BLOCK_M + row_in_tile;  // row within the batch
       const bool row_ok = r < p.rows_valid;
       const long orow = (long)c.batch * p.out_batch_pitch + (long)(r + p.out_row_offset) * p.ldo;
+      const int ch0 = half * CH_PER_WARP;
+      // while the MMAs of this tile run: stage the tile's bias slice in smem, prefetch the first chunk's residual / pos rows
+      float* sb = s_bias + acc_stage * BLOCK_N;
+      for (int i = etid; i < BLOCK_N; i += kEpiThreads) {
+        const int n = c.n_blk * BLOCK_N + i;
+        sb[i] = (p.bias != nullptr && n < p.N) ? p.bias[n] : 0.f;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      float4 extra[2][8];
+      auto load_extra = [&](float4(&dst)[8], int ch) {
+        if constexpr (kHasExtra) {
+          const int n0 = c.n_blk * BLOCK_N + ch * 32;
+          const float* src = (EPI == EPI_BIAS_RESID_F32) ? reinterpret_cast<const float*>(p.out) + orow + n0 : p.pos + (long)r * p.N + n0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            dst[j] = (row_ok && n0 + j * 4 + 4 <= p.N) ? *reinterpret_cast<const float4*>(src + j * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      load_extra(extra[0], ch0);
+      mbar_wait(&tmem_full_bar[acc_stage], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + acc_stage * BLOCK_N;
+      uint32_t v[2][32];
+      tmem_ld_32x32b_x32(tbase + ch0 * 32, v[0]);
       float best = -FLT_MAX;
       int best_idx = 0x7fffffff;
-#pragma unroll 1
-      for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
-        uint32_t v[32];
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + acc_stage * BLOCK_N + ch * 32;
-        tmem_ld_32x32b_x32(taddr, v);
+#pragma unroll
+      for (int i = 0; i < CH_PER_WARP; ++i) {
+        const int ch = ch0 + i;
         tcgen05_wait_ld();
+        if (i + 1 < CH_PER_WARP) {  // next chunk's TMEM read and residual loads fly while this chunk is processed
+          tmem_ld_32x32b_x32(tbase + (ch + 1) * 32, v[(i + 1) & 1]);
+          load_extra(extra[(i + 1) & 1], ch + 1);
+        }
         const int n0 = c.n_blk * BLOCK_N + ch * 32;
         if (!row_ok || n0 >= p.N) continue;
         float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (n0 + j < p.N) {
-              const float4 bv = *reinterpret_cast<const float4*>(p.bias + n0 + j);
-              f[j] += bv.x, f[j + 1] += bv.y, f[j + 2] += bv.z, f[j + 3] += bv.w;
-            }
-          }
+        for (int j = 0; j < 32; j += 4) {
+          const float4 bv = *reinterpret_cast<const float4*>(sb + ch * 32 + j);
+          f[j] = __uint_as_float(v[i & 1][j]) + bv.x, f[j + 1] = __uint_as_float(v[i & 1][j + 1]) + bv.y;
+          f[j + 2] = __uint_as_float(v[i & 1][j + 2]) + bv.z, f[j + 3] = __uint_as_float(v[i & 1][j + 3]) + bv.w;
         }
         const bool full = n0 + 32 <= p.N;
         if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
           if constexpr (EPI == EPI_BIAS_GELU_BF16) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+            for (int j = 0; j < 32; ++j) f[j] = gelu_fast(f[j]);
           }
           __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + orow + n0;
           if (full) {
@@ -218,34 +250,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         } else if constexpr (EPI == EPI_BIAS_F32 || EPI == EPI_BIAS_RESID_F32 || EPI == EPI_GELU_POS_F32) {
           float* o = reinterpret_cast<float*>(p.out) + orow + n0;
           if constexpr (EPI == EPI_GELU_POS_F32) {
-            const float* pe = p.pos + (long)r * p.N + n0;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (n0 + j < p.N) {
-                const float4 pv = *reinterpret_cast<const float4*>(pe + j);
-                f[j] = gelu_erf(f[j]) + pv.x, f[j + 1] = gelu_erf(f[j + 1]) + pv.y;
-                f[j + 2] = gelu_erf(f[j + 2]) + pv.z, f[j + 3] = gelu_erf(f[j + 3]) + pv.w;
-              }
-            }
+            for (int j = 0; j < 32; ++j) f[j] = gelu_fast(f[j]);
           }
           if (full) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               float4 u = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-              if constexpr (EPI == EPI_BIAS_RESID_F32) {
-                const float4 rv = *reinterpret_cast<const float4*>(o + j);
+              if constexpr (kHasExtra) {
+                const float4 rv = extra[i & 1][j >> 2];
                 u.x += rv.x, u.y += rv.y, u.z += rv.z, u.w += rv.w;
               }
               *reinterpret_cast<float4*>(o + j) = u;
             }
           } else {
+            const float* xs = (EPI == EPI_GELU_POS_F32) ? p.pos + (long)r * p.N + n0 : o;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.N) o[j] = (EPI == EPI_BIAS_RESID_F32 ? o[j] : 0.f) + f[j];
+              if (n0 + j < p.N) o[j] = (kHasExtra ? xs[j] : 0.f) + f[j];
           }
         } else if constexpr (EPI == EPI_CROSSKV_BF16) {
           // n0 is 32-aligned, so the chunk stays inside one (layer, k|v, head) slice of 64 columns
-          const int which = n0 / p.d_model;          // layer * 2 + kv
+          const int which = n0 / p.d_model;  // layer * 2 + kv
           const int within = n0 - which * p.d_model;
           const int h = within >> 6, dh = within & 63;
           const int layer = which >> 1;
@@ -277,7 +303,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
       if constexpr (EPI == EPI_ARGMAX) {
         if (row_ok) {
-          const long pi = ((long)c.batch * p.rows_valid + r) * p.part_ld + c.n_blk;
+          const long pi = ((long)c.batch * p.rows_valid + r) * p.part_ld + c.n_blk * (kEpiWarps / 4) + half;
           p.part_val[pi] = best;
           p.part_idx[pi] = best_idx;
         }
@@ -343,8 +369,12 @@ CUtensorMap make_tmap(const void* base, int rank, const uint64_t* dims, const ui
 template <int BLOCK_N, int EPI>
 void launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmGeom& g, const GemmParams& p, int grid, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
-  gemm_tcgen05_kernel<BLOCK_N, EPI><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, g, p);
-  CUDA_CHECK(cudaGetLastError());
+  if (p.use_pdl) {
+    launch_pdl(gemm_tcgen05_kernel<BLOCK_N, EPI>, dim3(grid), dim3(Cfg::kThreads), (size_t)Cfg::kSmemBytes, stream, ta, tb, g, p);
+  } else {
+    gemm_tcgen05_kernel<BLOCK_N, EPI><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, g, p);
+    CUDA_CHECK(cudaGetLastError());
+  }
 }
 
 template <int EPI>

@@ -66,6 +66,7 @@ struct GemmParams {
   int out_row_offset;    // added to the row index within a batch (conv1 writes into a padded buffer)
   int a_batch_offset;    // added to the batch coordinate of A (sub-batches of a larger resident tensor)
   int n_batch;           // batches in this launch (<= the plan's n_batch)
+  int use_pdl;           // launch with programmatic dependent launch (decoder-step GEMMs)
   const float* bias;     // [N] or null
   const float* pos;      // EPI_GELU_POS_F32: [rows_valid][N] f32
   // EPI_CROSSKV_BF16: n = (layer*2 + kv)*d + h*64 + dh ; row = (batch b, t)
