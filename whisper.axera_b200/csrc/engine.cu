@@ -171,6 +171,8 @@ Engine::Engine(const std::string& model_root, const std::string& model_type, int
   const std::string dir = model_root + "/" + model_type;  // {root}/{type}/{type}-*  (Whisper.cpp:87-90)
   cfg_ = load_model_config(model_root, model_type);
 
+  const char* attn_env = getenv("B200W_ATTN");
+  attn_mma_sync_ = attn_env != nullptr && std::string(attn_env) == "mma_sync";
   logmel_upload_tables();
   kernels_set_attributes();
   load_weights(dir, model_type);
@@ -473,7 +475,10 @@ void Engine::run_encoder(int B) {
       p = GemmParams{};
       p.rows_valid = rows, p.N = 3 * d, p.out = qkv_enc_, p.ldo = 3 * d, p.bias = L.b_qkv, p.n_batch = 1;
       gemm_launch(enc_plans_[i].qkv, p, stream_);
-      launch_encoder_attention(qkv_enc_, attn_enc_, nb, kAudioCtx, H, stream_);
+      if (attn_mma_sync_)
+        launch_encoder_attention(qkv_enc_, attn_enc_, nb, kAudioCtx, H, stream_);  // bring-up comparator (B200W_ATTN=mma_sync)
+      else
+        launch_encoder_attention_tcgen05(qkv_enc_, attn_enc_, nb, kAudioCtx, H, stream_);
       p = GemmParams{};
       p.rows_valid = rows, p.N = d, p.out = x_enc_, p.ldo = d, p.bias = L.b_out, p.n_batch = 1;
       gemm_launch(enc_plans_[i].out, p, stream_);

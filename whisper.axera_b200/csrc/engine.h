@@ -122,6 +122,7 @@ class Engine {
   cudaStream_t stream_ = nullptr;
   int cap_ = 0;
   int enc_sub_ = 0;
+  bool attn_mma_sync_ = false;
   long pcm_stride_ = 0;
   long launches_ = 0;
 

@@ -344,7 +344,9 @@ PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-CUtensorMap make_tmap(const void* base, int rank, const uint64_t* dims, const uint64_t* pitches_bytes, const uint32_t* box) {
+}  // namespace
+
+CUtensorMap make_tmap_bf16_sw128(const void* base, int rank, const uint64_t* dims, const uint64_t* pitches_bytes, const uint32_t* box) {
   CUtensorMap m;
   cuuint64_t gdim[3], gstr[2];
   cuuint32_t bdim[3], estr[3];
@@ -364,6 +366,11 @@ CUtensorMap make_tmap(const void* base, int rank, const uint64_t* dims, const ui
     throw CudaError(buf);
   }
   return m;
+}
+
+namespace {
+inline CUtensorMap make_tmap(const void* base, int rank, const uint64_t* dims, const uint64_t* pitches_bytes, const uint32_t* box) {
+  return make_tmap_bf16_sw128(base, rank, dims, pitches_bytes, box);
 }
 
 template <int BLOCK_N, int EPI>

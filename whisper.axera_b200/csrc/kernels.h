@@ -14,10 +14,12 @@ namespace b200w {
 void gemm_set_attributes();
 void logmel_set_attributes();
 void encoder_ops_set_attributes();
+void attention_tcgen05_set_attributes();
 inline void kernels_set_attributes() {
   gemm_set_attributes();
   logmel_set_attributes();
   encoder_ops_set_attributes();
+  attention_tcgen05_set_attributes();
 }
 
 // ---- K1 log-mel (logmel.cu) -----------------------------------------------------------------------
@@ -87,11 +89,16 @@ void gemm_launch(const GemmPlan* plan, const GemmParams& p, cudaStream_t stream)
 void gemm_reference_simt(const __nv_bfloat16* a, long lda, const __nv_bfloat16* w, long ldw, const float* bias, float* out,
                          long ldo, int M, int N, int K, cudaStream_t stream);
 
+// bf16 tiled tensor map with SWIZZLE_128B (rank 2 or 3; dims / box innermost first; pitches in bytes for dims 1..)
+CUtensorMap make_tmap_bf16_sw128(const void* base, int rank, const uint64_t* dims, const uint64_t* pitches_bytes, const uint32_t* box);
+
 // ---- encoder ops (encoder_ops.cu) -----------------------------------------------------------------
 // LayerNorm (eps 1e-5, fp32 statistics): x f32 [rows][d] -> y bf16 [rows][d]
 void launch_layernorm(const float* x, const float* gamma, const float* beta, __nv_bfloat16* y, int rows, int d, cudaStream_t stream);
 // non-causal multi-head attention over T keys, head_dim 64: qkv bf16 [B*T][3d] -> out bf16 [B*T][d]
-void launch_encoder_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int n_head, cudaStream_t stream);
+void launch_encoder_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int n_head, cudaStream_t stream);  // mma.sync comparator
+// same contract on tcgen05 tensor cores (attention_tcgen05.cu); this is the product path
+void launch_encoder_attention_tcgen05(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int n_head, cudaStream_t stream);
 
 // ---- decode ops (decode_ops.cu) -------------------------------------------------------------------
 struct DecodeState {

@@ -284,6 +284,48 @@ int b200w_mel_tables(int n_mels, float* bank, float* window) {
   return 0;
 }
 
+// tcgen05 attention against the mma.sync comparator kernel on random bf16 q/k/v ([B*T][3d], head_dim 64).
+int b200w_selftest_attention(int B, int T, int n_head, unsigned seed, float* max_abs_diff, float* max_abs_ref) {
+  if (!max_abs_diff || !max_abs_ref) return -1;
+  return guarded([&] {
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) throw CudaError("no CUDA device");
+    kernels_set_attributes();
+    const int d = n_head * 64;
+    const size_t n_in = (size_t)B * T * 3 * d, n_out = (size_t)B * T * d;
+    std::mt19937 rng(seed);
+    std::normal_distribution<float> nd(0.f, 1.f);
+    std::vector<__nv_bfloat16> h(n_in);
+    for (size_t i = 0; i < n_in; ++i) h[i] = __float2bfloat16(nd(rng) * ((i / d) % 3 == 2 ? 1.0f : 1.5f));
+    __nv_bfloat16 *dq, *o1, *o2;
+    CUDA_CHECK(cudaMalloc(&dq, n_in * 2));
+    CUDA_CHECK(cudaMalloc(&o1, n_out * 2));
+    CUDA_CHECK(cudaMalloc(&o2, n_out * 2));
+    CUDA_CHECK(cudaMemcpy(dq, h.data(), n_in * 2, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemset(o1, 0, n_out * 2));
+    CUDA_CHECK(cudaMemset(o2, 0, n_out * 2));
+    cudaStream_t s;
+    CUDA_CHECK(cudaStreamCreate(&s));
+    launch_encoder_attention(dq, o1, B, T, n_head, s);
+    launch_encoder_attention_tcgen05(dq, o2, B, T, n_head, s);
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    std::vector<__nv_bfloat16> a(n_out), b(n_out);
+    CUDA_CHECK(cudaMemcpy(a.data(), o1, n_out * 2, cudaMemcpyDeviceToHost));
+    CUDA_CHECK(cudaMemcpy(b.data(), o2, n_out * 2, cudaMemcpyDeviceToHost));
+    double md = 0, mr = 0;
+    for (size_t i = 0; i < n_out; ++i) {
+      const float x = __bfloat162float(a[i]), y = __bfloat162float(b[i]);
+      if (!(y == y)) md = 1e9;  // NaN
+      md = std::max(md, (double)fabsf(x - y));
+      mr = std::max(mr, (double)fabsf(x));
+    }
+    *max_abs_diff = (float)md;
+    *max_abs_ref = (float)mr;
+    cudaStreamDestroy(s);
+    cudaFree(dq), cudaFree(o1), cudaFree(o2);
+  });
+}
+
 // tcgen05 GEMM vs SIMT comparator on random bf16 data.  Epilogues covered here: EPI_BIAS_F32 (2), EPI_BIAS_BF16 (0),
 // EPI_BIAS_GELU_BF16 (1), EPI_BIAS_RESID_F32 (3), EPI_ARGMAX (6).
 int b200w_selftest_gemm(int M, int N, int K, int block_n, int epilogue, unsigned seed, float* max_abs_diff, float* max_abs_ref) {
