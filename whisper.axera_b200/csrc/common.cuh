@@ -42,6 +42,17 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
 }
+// same, with the programmatic attribute only if `pdl` (kernels that follow a cross-stream event wait launch plainly)
+template <class... KArgs, class... Args>
+inline void launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  if (pdl) {
+    launch_pdl(kernel, grid, block, smem, stream, static_cast<Args&&>(args)...);
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+    CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+  }
+}
 #endif
 
 #ifdef __CUDACC__

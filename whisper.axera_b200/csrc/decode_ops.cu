@@ -66,7 +66,7 @@ __device__ __forceinline__ void attend_one_query(const float* __restrict__ q_glo
 
   // ---- phase 1: scores ----
   float mx = -INFINITY;
-  constexpr int U = 4;  // independent 16-byte loads in flight per thread
+  constexpr int U = 8;  // independent 16-byte loads in flight per thread (3 CTAs/SM x 256 thr x 8 x 16 B = 98 KB in flight)
   for (int jb = warp * 4; jb < n; jb += NW * 4 * U) {  // warp-uniform bounds: the shuffles below need every lane
     const int j0 = jb + grp;
     uint4 kv[U];
@@ -281,35 +281,43 @@ __global__ void __launch_bounds__(kSelfWarps * 32) self_attention_decode_kernel(
 }
 
 // ---- cross attention ---------------------------------------------------------------------------------------
+// Persistent: at most kCrossCtasPerSm CTAs per SM walk the (sequence, head[, split]) work items.  Capping the resident
+// CTAs leaves threads / registers / smem on every SM for the small kernels of the OTHER micro-batch, which the engine
+// runs concurrently on a second stream (their latency hides under this HBM-bound stream).
 constexpr int kCrossThreads = 256;
+constexpr int kCrossCtasPerSm = 3;
 __global__ void __launch_bounds__(kCrossThreads) cross_attention_decode_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                                                                               const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ out,
-                                                                              int n_head, int T, int n_split, float* __restrict__ part_m,
+                                                                              int n_items, int n_head, int T, int n_split, float* __restrict__ part_m,
                                                                               float* __restrict__ part_l, float* __restrict__ part_o) {
   __shared__ float s_scores[kCrossThreads / 32 * 64 > 1504 ? kCrossThreads / 32 * 64 : 1504];
   __shared__ float s_red[kCrossThreads / 32];
   __shared__ float s_out[64];
   __shared__ float s_ml[2];
   pdl_wait();
-  const int h = blockIdx.x / n_split, sp = blockIdx.x % n_split;
-  const int b = blockIdx.y;
   const int d = n_head * 64;
-  const long kv_off = ((long)b * n_head + h) * T * 64;
   const int per = (T + n_split - 1) / n_split;
-  const int k_begin = sp * per, k_end = min(T, k_begin + per);
-  attend_one_query<kCrossThreads>(q + (long)b * d + h * 64, k + kv_off, v + kv_off, k_begin, k_end, nullptr, nullptr, s_scores, s_red,
-                                  s_out, s_ml);
-  pdl_launch_dependents();  // multi-wave kernel: let the successor start only in this CTA's tail
-  if (n_split == 1) {
-    if (threadIdx.x < 64) out[(long)b * d + h * 64 + threadIdx.x] = __float2bfloat16_rn(s_out[threadIdx.x] / s_ml[1]);
-  } else {
-    const long pi = ((long)b * n_head + h) * n_split + sp;
-    if (threadIdx.x < 64) part_o[pi * 64 + threadIdx.x] = s_out[threadIdx.x];
-    if (threadIdx.x == 0) {
-      part_m[pi] = s_ml[0];
-      part_l[pi] = s_ml[1];
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int sp = item % n_split;
+    const int bh = item / n_split;  // b * n_head + h
+    const int b = bh / n_head, h = bh - b * n_head;
+    const long kv_off = (long)bh * T * 64;
+    const int k_begin = sp * per, k_end = min(T, k_begin + per);
+    attend_one_query<kCrossThreads>(q + (long)b * d + h * 64, k + kv_off, v + kv_off, k_begin, k_end, nullptr, nullptr, s_scores, s_red,
+                                    s_out, s_ml);
+    if (n_split == 1) {
+      if (threadIdx.x < 64) out[(long)b * d + h * 64 + threadIdx.x] = __float2bfloat16_rn(s_out[threadIdx.x] / s_ml[1]);
+    } else {
+      const long pi = (long)bh * n_split + sp;
+      if (threadIdx.x < 64) part_o[pi * 64 + threadIdx.x] = s_out[threadIdx.x];
+      if (threadIdx.x == 0) {
+        part_m[pi] = s_ml[0];
+        part_l[pi] = s_ml[1];
+      }
     }
+    __syncthreads();  // s_out / s_ml are rewritten by the next item
   }
+  pdl_launch_dependents();
 }
 
 __global__ void cross_attention_combine_kernel(const float* __restrict__ part_m, const float* __restrict__ part_l,
@@ -379,8 +387,8 @@ bool pdl_enabled() {
 }
 
 void launch_embed(const DecodeState& st, const float* tok_emb, const float* pos_emb, float* x, int B, int d, int n_text_ctx,
-                  cudaStream_t stream) {
-  launch_pdl(embed_kernel, dim3(B), dim3(128), 0, stream, st.step, st.tokens, tok_emb, pos_emb, x, d, n_text_ctx);
+                  cudaStream_t stream, bool pdl) {
+  launch_k(pdl, embed_kernel, dim3(B), dim3(128), 0, stream, st.step, st.tokens, tok_emb, pos_emb, x, d, n_text_ctx);
 }
 
 void launch_self_attention_decode(const float* qkv, __nv_bfloat16* k_cache, __nv_bfloat16* v_cache, const int* step, __nv_bfloat16* out,
@@ -398,16 +406,19 @@ int cross_attention_pick_split(int B, int n_head) {
 }
 
 void launch_cross_attention_decode(const float* q, const __nv_bfloat16* k, const __nv_bfloat16* v, __nv_bfloat16* out, int B, int n_head,
-                                   int T, int n_split, float* part_m, float* part_l, float* part_o, cudaStream_t stream) {
-  dim3 grid(n_head * n_split, B);
-  launch_pdl(cross_attention_decode_kernel, grid, dim3(kCrossThreads), 0, stream, q, k, v, out, n_head, T, n_split, part_m, part_l, part_o);
+                                   int T, int n_split, float* part_m, float* part_l, float* part_o, cudaStream_t stream, bool pdl) {
+  const int n_items = B * n_head * n_split;
+  const int grid = n_items < kCrossCtasPerSm * kNumSMs ? n_items : kCrossCtasPerSm * kNumSMs;
+  launch_k(pdl, cross_attention_decode_kernel, dim3(grid), dim3(kCrossThreads), 0, stream, q, k, v, out, n_items, n_head, T, n_split, part_m,
+           part_l, part_o);
   if (n_split > 1) launch_pdl(cross_attention_combine_kernel, dim3(n_head, B), dim3(64), 0, stream, part_m, part_l, part_o, out, n_head, n_split);
 }
 
 void launch_argmax_finalize(const DecodeState& st, const float* part_val, const int* part_idx, int n_tiles, int part_ld, int B,
                             int n_text_ctx, int eot, int honor_eot, int sot_len, cudaStream_t stream) {
   launch_pdl(argmax_finalize_kernel, dim3(B), dim3(128), 0, stream, st, part_val, part_idx, n_tiles, part_ld, n_text_ctx, eot, honor_eot, sot_len);
-  launch_pdl(advance_step_kernel, dim3(1), dim3(1), 0, stream, st.step);
 }
+
+void launch_advance_step(int* step, cudaStream_t stream, bool pdl) { launch_k(pdl, advance_step_kernel, dim3(1), dim3(1), 0, stream, step); }
 
 }  // namespace b200w

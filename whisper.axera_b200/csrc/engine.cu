@@ -166,6 +166,8 @@ Engine::Engine(const std::string& model_root, const std::string& model_type, int
   CUDA_CHECK(cudaGetDeviceProperties(&prop, device_));
   if (prop.major != 10) throw CudaError(std::string("this build contains sm_100a code only; device is ") + prop.name);
   CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  CUDA_CHECK(cudaStreamCreateWithFlags(&stream2_, cudaStreamNonBlocking));
+  micro_batch_ = getenv("B200W_NO_MICROBATCH") == nullptr;
   CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&pinned_flags_), 4096 * sizeof(int)));
 
   const std::string dir = model_root + "/" + model_type;  // {root}/{type}/{type}-*  (Whisper.cpp:87-90)
@@ -176,6 +178,8 @@ Engine::Engine(const std::string& model_root, const std::string& model_type, int
   logmel_upload_tables();
   kernels_set_attributes();
   load_weights(dir, model_type);
+  step_events_.resize(2 + 2 * cfg_.l_dec);
+  for (auto& e : step_events_) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   ensure_capacity(std::max(1, max_batch));
 }
 
@@ -185,6 +189,8 @@ Engine::~Engine() {
   free_workspace();  // also destroys the captured decode graphs
   for (void* p : owned_) cudaFree(p);
   if (pinned_flags_) cudaFreeHost(pinned_flags_);
+  for (auto& e : step_events_) cudaEventDestroy(e);
+  if (stream2_) cudaStreamDestroy(stream2_);
   if (stream_) cudaStreamDestroy(stream_);
 }
 
@@ -500,41 +506,102 @@ void Engine::run_encoder(int B) {
   }
 }
 
-void Engine::enqueue_decode_step(int B, bool want_logits) {
-  const int d = cfg_.d, H = cfg_.n_head;
-  const int n_split = cross_attention_pick_split(B, H);
-  launch_embed(st_, emb_f32_, pos_text_, x_dec_, B, d, kTextCtx, stream_);
-  launches_ += 1;
-  GemmParams p{};
-  auto gp = [&](void* out, long ldo, int N, const float* bias) {
+// One decoder step for B sequences.  With B >= 32 the batch is split into two micro-batches on two streams: while one
+// micro-batch streams its cross-attention K/V (HBM-bound, all SMs but capped at 3 CTAs each), the other runs its chain of
+// small latency-bound kernels (LayerNorm, M<=128 GEMMs, self attention).  Events hand the HBM "token" back and forth so the
+// two cross-attention kernels alternate instead of competing; sequences are independent, so results do not change.
+void Engine::enqueue_decode_step(int B, bool want_logits, bool finalize, int honor_eot) {
+  const int d = cfg_.d, H = cfg_.n_head, Ld = cfg_.l_dec;
+  const int n_mb = (micro_batch_ && B >= 32) ? 2 : 1;
+  struct MB {
+    int b0, nb;
+    cudaStream_t s;
+  } mb[2];
+  mb[0] = {0, n_mb == 2 ? (B + 1) / 2 : B, stream_};
+  mb[1] = {mb[0].nb, B - mb[0].nb, stream2_};
+  cudaEvent_t ev_fork = step_events_[0], ev_join = step_events_[1];
+  if (n_mb == 2) {
+    CUDA_CHECK(cudaEventRecord(ev_fork, stream_));
+    CUDA_CHECK(cudaStreamWaitEvent(stream2_, ev_fork, 0));
+  }
+  auto gp = [&](const MB& m, void* out, size_t elem, long ldo, int N, const float* bias) {
     GemmParams q{};
-    q.rows_valid = B, q.N = N, q.out = out, q.ldo = ldo, q.bias = bias, q.n_batch = 1, q.use_pdl = 1;
+    q.rows_valid = m.nb, q.N = N, q.out = static_cast<char*>(out) + (size_t)m.b0 * ldo * elem, q.ldo = ldo, q.bias = bias, q.n_batch = 1;
+    q.use_pdl = 1, q.a_row_offset = m.b0;
     return q;
   };
-  for (int l = 0; l < cfg_.l_dec; ++l) {
+  for (int i = 0; i < n_mb; ++i) {
+    DecodeState st = st_;
+    st.tokens += (size_t)mb[i].b0 * kTextCtx;
+    launch_embed(st, emb_f32_, pos_text_, x_dec_ + (size_t)mb[i].b0 * d, mb[i].nb, d, kTextCtx, mb[i].s, /*pdl=*/n_mb == 1);
+  }
+  launches_ += n_mb;
+  for (int l = 0; l < Ld; ++l) {
     const LayerDec& L = dec_[l];
     const DecPlans& P = dec_plans_[l];
-    const size_t skv_off = (size_t)l * cap_ * H * kTextCtx * 64;
-    const size_t ckv_off = (size_t)l * cap_ * H * kAudioCtx * 64;
-    launch_layernorm(x_dec_, L.ln1_g, L.ln1_b, h_dec_, B, d, stream_);
-    gemm_launch(P.qkv, gp(qkv_dec_, 3 * d, 3 * d, L.b_qkv), stream_);
-    launch_self_attention_decode(qkv_dec_, self_k_ + skv_off, self_v_ + skv_off, st_.step, attn_dec_, B, H, kTextCtx, stream_);
-    gemm_launch(P.out, gp(x_dec_, d, d, L.b_out), stream_);
-    launch_layernorm(x_dec_, L.lnx_g, L.lnx_b, h_dec_, B, d, stream_);
-    gemm_launch(P.cq, gp(q_dec_, d, d, L.b_cq), stream_);
-    launch_cross_attention_decode(q_dec_, cross_k_ + ckv_off, cross_v_ + ckv_off, attn_dec_, B, H, kAudioCtx, n_split, part_m_, part_l_,
-                                  part_o_, stream_);
-    gemm_launch(P.co, gp(x_dec_, d, d, L.b_co), stream_);
-    launch_layernorm(x_dec_, L.ln2_g, L.ln2_b, h_dec_, B, d, stream_);
-    gemm_launch(P.fc1, gp(mlp_dec_, 4 * d, 4 * d, L.b_fc1), stream_);
-    gemm_launch(P.fc2, gp(x_dec_, d, d, L.b_fc2), stream_);
-    launches_ += 11 + (n_split > 1 ? 1 : 0);
+    for (int i = 0; i < n_mb; ++i) {
+      const MB& m = mb[i];
+      const size_t skv_off = ((size_t)l * cap_ + m.b0) * H * kTextCtx * 64;
+      float* x = x_dec_ + (size_t)m.b0 * d;
+      __nv_bfloat16* h = h_dec_ + (size_t)m.b0 * d;
+      launch_layernorm(x, L.ln1_g, L.ln1_b, h, m.nb, d, m.s);
+      gemm_launch(P.qkv, gp(m, qkv_dec_, 4, 3 * d, 3 * d, L.b_qkv), m.s);
+      launch_self_attention_decode(qkv_dec_ + (size_t)m.b0 * 3 * d, self_k_ + skv_off, self_v_ + skv_off, st_.step,
+                                   attn_dec_ + (size_t)m.b0 * d, m.nb, H, kTextCtx, m.s);
+      gemm_launch(P.out, gp(m, x_dec_, 4, d, d, L.b_out), m.s);
+      launch_layernorm(x, L.lnx_g, L.lnx_b, h, m.nb, d, m.s);
+      gemm_launch(P.cq, gp(m, q_dec_, 4, d, d, L.b_cq), m.s);
+    }
+    for (int i = 0; i < n_mb; ++i) {
+      const MB& m = mb[i];
+      const int n_split = cross_attention_pick_split(m.nb, H);
+      const size_t ckv_off = ((size_t)l * cap_ + m.b0) * H * kAudioCtx * 64;
+      const size_t po = (size_t)m.b0 * H * 8;
+      if (n_mb == 2) {
+        // micro-batch 0 waits for micro-batch 1's previous cross attention, micro-batch 1 for micro-batch 0's current one
+        if (i == 0 && l > 0) CUDA_CHECK(cudaStreamWaitEvent(m.s, step_events_[2 + 2 * (l - 1) + 1], 0));
+        if (i == 1) CUDA_CHECK(cudaStreamWaitEvent(m.s, step_events_[2 + 2 * l], 0));
+      }
+      launch_cross_attention_decode(q_dec_ + (size_t)m.b0 * d, cross_k_ + ckv_off, cross_v_ + ckv_off, attn_dec_ + (size_t)m.b0 * d, m.nb, H,
+                                    kAudioCtx, n_split, part_m_ + po, part_l_ + po, part_o_ + po * 64, m.s, /*pdl=*/n_mb == 1);
+      if (n_mb == 2) CUDA_CHECK(cudaEventRecord(step_events_[2 + 2 * l + i], m.s));
+      launches_ += 1 + (n_split > 1 ? 1 : 0);
+    }
+    for (int i = 0; i < n_mb; ++i) {
+      const MB& m = mb[i];
+      float* x = x_dec_ + (size_t)m.b0 * d;
+      __nv_bfloat16* h = h_dec_ + (size_t)m.b0 * d;
+      gemm_launch(P.co, gp(m, x_dec_, 4, d, d, L.b_co), m.s);
+      launch_layernorm(x, L.ln2_g, L.ln2_b, h, m.nb, d, m.s);
+      gemm_launch(P.fc1, gp(m, mlp_dec_, 2, 4 * d, 4 * d, L.b_fc1), m.s);
+      gemm_launch(P.fc2, gp(m, x_dec_, 4, d, d, L.b_fc2), m.s);
+    }
+    launches_ += 10 * n_mb;
   }
-  launch_layernorm(x_dec_, dec_ln_g_, dec_ln_b_, h_dec_, B, d, stream_);
-  p = gp(want_logits ? logits_ : nullptr, vocab_pad_, cfg_.n_vocab, nullptr);
-  p.part_val = part_val_, p.part_idx = part_idx_, p.part_ld = logits_tiles_;
-  gemm_launch(p_logits_, p, stream_);
-  launches_ += 2;
+  for (int i = 0; i < n_mb; ++i) {
+    const MB& m = mb[i];
+    launch_layernorm(x_dec_ + (size_t)m.b0 * d, dec_ln_g_, dec_ln_b_, h_dec_ + (size_t)m.b0 * d, m.nb, d, m.s);
+    GemmParams p = gp(m, want_logits ? logits_ : nullptr, 4, vocab_pad_, cfg_.n_vocab, nullptr);
+    if (!want_logits) p.out = nullptr;
+    p.part_val = part_val_ + (size_t)m.b0 * logits_tiles_, p.part_idx = part_idx_ + (size_t)m.b0 * logits_tiles_, p.part_ld = logits_tiles_;
+    gemm_launch(p_logits_, p, m.s);
+    launches_ += 2;
+    if (finalize) {
+      DecodeState st = st_;
+      st.tokens += (size_t)m.b0 * kTextCtx, st.forced += (size_t)m.b0 * kTextCtx, st.out_tokens += (size_t)m.b0 * kTextCtx;
+      st.finished += m.b0;
+      launch_argmax_finalize(st, p.part_val, p.part_idx, logits_tiles_, logits_tiles_, m.nb, kTextCtx, cfg_.eot, honor_eot, kSotLen, m.s);
+      launches_ += 1;
+    }
+  }
+  if (n_mb == 2) {
+    CUDA_CHECK(cudaEventRecord(ev_join, stream2_));
+    CUDA_CHECK(cudaStreamWaitEvent(stream_, ev_join, 0));
+  }
+  if (finalize) {
+    launch_advance_step(st_.step, stream_, /*pdl=*/n_mb == 1);
+    launches_ += 1;
+  }
 }
 
 void Engine::run_cross_attention_only(int B) {
@@ -583,8 +650,8 @@ int Engine::run_decode(int B, const std::vector<int>& sot, const DecodeOptions& 
       cudaGraph_t g;
       CUDA_CHECK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
       const long before = launches_;
-      enqueue_decode_step(B, false);
-      launch_argmax_finalize(st_, part_val_, part_idx_, logits_tiles_, logits_tiles_, B, kTextCtx, cfg_.eot, opt.honor_eot ? 1 : 0, kSotLen, stream_);
+      enqueue_decode_step(B, false, true, opt.honor_eot ? 1 : 0);
+      per_step_launches_[key] = launches_ - before;
       launches_ = before;  // capture does not launch
       CUDA_CHECK(cudaStreamEndCapture(stream_, &g));
       CUDA_CHECK(cudaGraphInstantiate(&exec, g, 0));
@@ -594,17 +661,14 @@ int Engine::run_decode(int B, const std::vector<int>& sot, const DecodeOptions& 
       exec = it->second;
     }
   }
-  const int n_split = cross_attention_pick_split(B, cfg_.n_head);
-  const long per_step = 1 + (long)cfg_.l_dec * (11 + (n_split > 1 ? 1 : 0)) + 2 + 2;
+  const long per_step = graph ? per_step_launches_[B * 2 + (opt.honor_eot ? 1 : 0)] : 0;
   int steps_done = 0;
   for (int s = 0; s < n_steps; ++s) {
     if (graph) {
       CUDA_CHECK(cudaGraphLaunch(exec, stream_));
       launches_ += per_step;
     } else {
-      enqueue_decode_step(B, want_logits);
-      launch_argmax_finalize(st_, part_val_, part_idx_, logits_tiles_, logits_tiles_, B, kTextCtx, cfg_.eot, opt.honor_eot ? 1 : 0, kSotLen, stream_);
-      launches_ += 2;
+      enqueue_decode_step(B, want_logits, true, opt.honor_eot ? 1 : 0);
       if (want_logits && s >= kSotLen - 1 && s - (kSotLen - 1) < max_new) {
         // logits after consuming position s = prediction of generated token (s - 3)
         CUDA_CHECK(cudaMemcpy2DAsync(opt.logits_out + (size_t)(s - (kSotLen - 1)) * B * cfg_.n_vocab, (size_t)cfg_.n_vocab * 4, logits_,
@@ -647,7 +711,7 @@ void Engine::decode_step_tokens(int B, const int* tokens_host, int offset, float
   CUDA_CHECK(cudaMemcpy2DAsync(st_.tokens + offset, kTextCtx * sizeof(int), col.data(), sizeof(int), sizeof(int), B, cudaMemcpyHostToDevice, stream_));
   CUDA_CHECK(cudaMemcpyAsync(st_.step, &offset, sizeof(int), cudaMemcpyHostToDevice, stream_));
   CUDA_CHECK(cudaStreamSynchronize(stream_));
-  enqueue_decode_step(B, true);
+  enqueue_decode_step(B, true, false, 0);
   if (logits_host)
     CUDA_CHECK(cudaMemcpy2DAsync(logits_host, (size_t)cfg_.n_vocab * 4, logits_, (size_t)vocab_pad_ * 4, (size_t)cfg_.n_vocab * 4, B,
                                  cudaMemcpyDeviceToHost, stream_));

@@ -115,11 +115,14 @@ class Engine {
   void load_weights(const std::string& dir, const std::string& type);
   void free_workspace();
   void build_plans();
-  void enqueue_decode_step(int B, bool want_logits);
+  void enqueue_decode_step(int B, bool want_logits, bool finalize, int honor_eot);
 
   ModelConfig cfg_;
   int device_ = 0;
   cudaStream_t stream_ = nullptr;
+  cudaStream_t stream2_ = nullptr;          // second micro-batch of a decoder step
+  std::vector<cudaEvent_t> step_events_;    // fork / join / per-layer cross-attention hand-over
+  bool micro_batch_ = true;
   int cap_ = 0;
   int enc_sub_ = 0;
   bool attn_mma_sync_ = false;
@@ -164,6 +167,7 @@ class Engine {
   std::vector<DecPlans> dec_plans_;
   // decode graph cache (keyed by batch size)
   std::map<int, cudaGraphExec_t> graphs_;
+  std::map<int, long> per_step_launches_;
   int* pinned_flags_ = nullptr;
 };
 

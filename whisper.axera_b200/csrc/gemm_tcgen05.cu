@@ -120,7 +120,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             unsigned char* sa = smem + stage * Cfg::kStageBytes;
             unsigned char* sb = sa + Cfg::kStageBytesA;
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-            tma_load_3d(sa, &tmap_a, &full_bar[stage], g.a_c0[tap] + kb * BLOCK_K, c.m_blk * BLOCK_M + g.a_row[tap], c.batch + p.a_batch_offset);
+            tma_load_3d(sa, &tmap_a, &full_bar[stage], g.a_c0[tap] + kb * BLOCK_K, c.m_blk * BLOCK_M + g.a_row[tap] + p.a_row_offset, c.batch + p.a_batch_offset);
             tma_load_2d(sb, &tmap_b, &full_bar[stage], g.w_k0[tap] + kb * BLOCK_K, c.n_blk * BLOCK_N);
             if (++stage == kStages) {
               stage = 0;

@@ -67,6 +67,7 @@ struct GemmParams {
   long out_batch_pitch;  // output elements between batches
   int out_row_offset;    // added to the row index within a batch (conv1 writes into a padded buffer)
   int a_batch_offset;    // added to the batch coordinate of A (sub-batches of a larger resident tensor)
+  int a_row_offset;      // added to the row coordinate of A (a launch over rows [a_row_offset, a_row_offset + rows_valid))
   int n_batch;           // batches in this launch (<= the plan's n_batch)
   int use_pdl;           // launch with programmatic dependent launch (decoder-step GEMMs)
   const float* bias;     // [N] or null
@@ -113,7 +114,7 @@ struct DecodeState {
 };
 // x[b] = tok_emb[token[b][step]] + pos_emb[step]      (f32)
 void launch_embed(const DecodeState& st, const float* tok_emb, const float* pos_emb, float* x, int B, int d, int n_text_ctx,
-                  cudaStream_t stream);
+                  cudaStream_t stream, bool pdl = true);
 // self attention for one new token per sequence over a bf16 head-major cache [B][H][n_ctx][64];
 // qkv f32 [B][3d] (q | k | v of the current token). Appends k,v at position *step, writes out bf16 [B][d].
 void launch_self_attention_decode(const float* qkv, __nv_bfloat16* k_cache, __nv_bfloat16* v_cache, const int* step,
@@ -122,8 +123,9 @@ void launch_self_attention_decode(const float* qkv, __nv_bfloat16* k_cache, __nv
 // part_* are workspaces for the split-T variant ([B*H*n_split] each, o is [..][64]).
 void launch_cross_attention_decode(const float* q, const __nv_bfloat16* k, const __nv_bfloat16* v, __nv_bfloat16* out, int B,
                                    int n_head, int T, int n_split, float* part_m, float* part_l, float* part_o,
-                                   cudaStream_t stream);
-// reduces the argmax partials, applies teacher forcing / EOT bookkeeping, stores the next token, bumps *step
+                                   cudaStream_t stream, bool pdl = true);
+// reduces the argmax partials, applies teacher forcing / EOT bookkeeping, stores the next token
+void launch_advance_step(int* step, cudaStream_t stream, bool pdl = true);  // *step += 1 (once per decoder step)
 void launch_argmax_finalize(const DecodeState& st, const float* part_val, const int* part_idx, int n_tiles, int part_ld, int B,
                             int n_text_ctx, int eot, int honor_eot, int sot_len, cudaStream_t stream);
 int cross_attention_pick_split(int B, int n_head);
