@@ -66,7 +66,7 @@ __device__ __forceinline__ void attend_one_query(const float* __restrict__ q_glo
 
   // ---- phase 1: scores ----
   float mx = -INFINITY;
-  constexpr int U = 8;  // independent 16-byte loads in flight per thread (3 CTAs/SM x 256 thr x 8 x 16 B = 98 KB in flight)
+  constexpr int U = 4;  // independent 16-byte loads in flight per thread (48 registers: 3 CTAs/SM leave room for a GEMM CTA)
   for (int jb = warp * 4; jb < n; jb += NW * 4 * U) {  // warp-uniform bounds: the shuffles below need every lane
     const int j0 = jb + grp;
     uint4 kv[U];

@@ -36,9 +36,12 @@ struct GemmCfg {
   static constexpr int kStageBytesA = BLOCK_M * BLOCK_K * 2;
   static constexpr int kStageBytesB = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-  static constexpr int kStages = kSmemBudget / kStageBytes;  // 256 -> 4, 128 -> 6, 64 -> 8, 32 -> 9
+  // the narrow tiles are the decoder-step GEMMs: they co-reside with the cross-attention CTAs of the other micro-batch,
+  // so they take less shared memory (6-7 stages) and fewer registers / threads
+  static constexpr int kStages = (BLOCK_N >= 128 ? kSmemBudget : 147456) / kStageBytes;  // 256 -> 4, 128 -> 6, 64 -> 6, 32 -> 7
   static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
-  static constexpr int kEpiWarps = BLOCK_N >= 64 ? 8 : 4;  // 8: two warps per TMEM lane group, each taking half of the columns
+  static constexpr int kEpiWarps = BLOCK_N >= 128 ? 8 : 4;  // 8: two warps per TMEM lane group, each taking half of the columns
+  static constexpr int kMinCtas = BLOCK_N >= 128 ? 1 : 2;    // register cap (<= 168) for the narrow tiles
   static constexpr int kThreads = 64 + 32 * kEpiWarps;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * BLOCK_N * 4 /*bias*/;
 };
@@ -65,7 +68,7 @@ __device__ __forceinline__ TileCoord tile_coord(int t, const GemmGeom& g) {
 }
 
 template <int BLOCK_N, int EPI>
-__global__ void __launch_bounds__(GemmCfg<BLOCK_N>::kThreads, 1)
+__global__ void __launch_bounds__(GemmCfg<BLOCK_N>::kThreads, GemmCfg<BLOCK_N>::kMinCtas)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmGeom g,
                     const GemmParams p) {
   using Cfg = GemmCfg<BLOCK_N>;

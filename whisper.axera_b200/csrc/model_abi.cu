@@ -357,7 +357,7 @@ int b200w_selftest_gemm(int M, int N, int K, int block_n, int epilogue, unsigned
     CUDA_CHECK(cudaMalloc(&dref, (size_t)M * N * 4));
     CUDA_CHECK(cudaMalloc(&dout, (size_t)M * N * 4));
     CUDA_CHECK(cudaMalloc(&dout_bf, (size_t)M * N * 2));
-    const int n_tiles = (N + block_n - 1) / block_n * (block_n >= 64 ? 2 : 1);  // arg-max partials per row
+    const int n_tiles = (N + block_n - 1) / block_n * (block_n >= 128 ? 2 : 1);  // arg-max partials per row
     CUDA_CHECK(cudaMalloc(&dpv, (size_t)M * n_tiles * 4));
     CUDA_CHECK(cudaMalloc(&dpi, (size_t)M * n_tiles * 4));
     CUDA_CHECK(cudaMemcpy(da, ha.data(), ha.size() * 2, cudaMemcpyHostToDevice));
