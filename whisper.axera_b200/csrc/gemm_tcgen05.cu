@@ -20,15 +20,15 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "gemm_common.cuh"
 #include "kernels.h"
 
 namespace b200w {
 
+using namespace gemm_detail;
+
 namespace {
 
-constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;   // 64 bf16 = 128 bytes = one swizzle row
-constexpr int UMMA_K = 16;
 constexpr int kSmemBudget = 196608;  // 192 KB of operand stages
 
 template <int BLOCK_N>
@@ -38,24 +38,12 @@ struct GemmCfg {
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
   // the narrow tiles are the decoder-step GEMMs: they co-reside with the cross-attention CTAs of the other micro-batch,
   // so they take less shared memory (6-7 stages) and fewer registers / threads
-  static constexpr int kStages = (BLOCK_N >= 128 ? kSmemBudget : 147456) / kStageBytes;  // 256 -> 4, 128 -> 6, 64 -> 6, 32 -> 7
+  static constexpr int kStages = (BLOCK_N >= 128 ? kSmemBudget : 98304) / kStageBytes;  // 256 -> 4, 128 -> 6, 64 -> 4, 32 -> 4
   static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
   static constexpr int kEpiWarps = BLOCK_N >= 128 ? 8 : 4;  // 8: two warps per TMEM lane group, each taking half of the columns
   static constexpr int kMinCtas = BLOCK_N >= 128 ? 1 : 2;    // register cap (<= 168) for the narrow tiles
   static constexpr int kThreads = 64 + 32 * kEpiWarps;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * BLOCK_N * 4 /*bias*/;
-};
-
-struct TileCoord {
-  int batch, m_blk, n_blk;
-};
-
-struct GemmGeom {
-  int m_tiles_per_batch, n_tiles, n_batch, num_k_blocks, total_tiles;
-  // implicit-GEMM convolution: the k loop runs over n_taps shifted views of A (tap t reads A columns
-  // a_c0[t] + k, rows row + a_row[t]) against W columns w_k0[t] + k.  A plain GEMM has one tap.
-  int n_taps, kb_per_tap;
-  int a_c0[3], a_row[3], w_k0[3];
 };
 
 __device__ __forceinline__ TileCoord tile_coord(int t, const GemmGeom& g) {
@@ -172,145 +160,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else {
     // ===== epilogue warps: TMEM lane group = warp % 4; with 8 warps each lane group's columns are split in two halves =====
     constexpr int kEpiWarps = Cfg::kEpiWarps;
-    constexpr int kEpiThreads = kEpiWarps * 32;
-    constexpr int CH_PER_WARP = (BLOCK_N / 32) / (kEpiWarps / 4);
-    constexpr bool kHasExtra = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_GELU_POS_F32);
-    const int lg = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const int etid = threadIdx.x - 64;
-    const int row_in_tile = lg * 32 + lane;
     float* s_bias = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + 256);  // [2][BLOCK_N]
     int acc_stage = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
       const TileCoord c = tile_coord(t, g);
-      const int r = c.m_blk * BLOCK_M + row_in_tile;  // row within the batch
-      const bool row_ok = r < p.rows_valid;
-      const long orow = (long)c.batch * p.out_batch_pitch + (long)(r + p.out_row_offset) * p.ldo;
-      const int ch0 = half * CH_PER_WARP;
-      // while the MMAs of this tile run: stage the tile's bias slice in smem, prefetch the first chunk's residual / pos rows
-      float* sb = s_bias + acc_stage * BLOCK_N;
-      for (int i = etid; i < BLOCK_N; i += kEpiThreads) {
-        const int n = c.n_blk * BLOCK_N + i;
-        sb[i] = (p.bias != nullptr && n < p.N) ? p.bias[n] : 0.f;
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-      float4 extra[2][8];
-      auto load_extra = [&](float4(&dst)[8], int ch) {
-        if constexpr (kHasExtra) {
-          const int n0 = c.n_blk * BLOCK_N + ch * 32;
-          const float* src = (EPI == EPI_BIAS_RESID_F32) ? reinterpret_cast<const float*>(p.out) + orow + n0 : p.pos + (long)r * p.N + n0;
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            dst[j] = (row_ok && n0 + j * 4 + 4 <= p.N) ? *reinterpret_cast<const float4*>(src + j * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      };
-      load_extra(extra[0], ch0);
-      mbar_wait(&tmem_full_bar[acc_stage], acc_phase);
-      tcgen05_fence_after();
-      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + acc_stage * BLOCK_N;
-      uint32_t v[2][32];
-      tmem_ld_32x32b_x32(tbase + ch0 * 32, v[0]);
-      float best = -FLT_MAX;
-      int best_idx = 0x7fffffff;
-#pragma unroll
-      for (int i = 0; i < CH_PER_WARP; ++i) {
-        const int ch = ch0 + i;
-        tcgen05_wait_ld();
-        if (i + 1 < CH_PER_WARP) {  // next chunk's TMEM read and residual loads fly while this chunk is processed
-          tmem_ld_32x32b_x32(tbase + (ch + 1) * 32, v[(i + 1) & 1]);
-          load_extra(extra[(i + 1) & 1], ch + 1);
-        }
-        const int n0 = c.n_blk * BLOCK_N + ch * 32;
-        if (!row_ok || n0 >= p.N) continue;
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 bv = *reinterpret_cast<const float4*>(sb + ch * 32 + j);
-          f[j] = __uint_as_float(v[i & 1][j]) + bv.x, f[j + 1] = __uint_as_float(v[i & 1][j + 1]) + bv.y;
-          f[j + 2] = __uint_as_float(v[i & 1][j + 2]) + bv.z, f[j + 3] = __uint_as_float(v[i & 1][j + 3]) + bv.w;
-        }
-        const bool full = n0 + 32 <= p.N;
-        if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
-          if constexpr (EPI == EPI_BIAS_GELU_BF16) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = gelu_fast(f[j]);
-          }
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + orow + n0;
-          if (full) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 u;
-              u.x = pack_bf16x2(f[j], f[j + 1]), u.y = pack_bf16x2(f[j + 2], f[j + 3]);
-              u.z = pack_bf16x2(f[j + 4], f[j + 5]), u.w = pack_bf16x2(f[j + 6], f[j + 7]);
-              *reinterpret_cast<uint4*>(o + j) = u;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.N) o[j] = __float2bfloat16_rn(f[j]);
-          }
-        } else if constexpr (EPI == EPI_BIAS_F32 || EPI == EPI_BIAS_RESID_F32 || EPI == EPI_GELU_POS_F32) {
-          float* o = reinterpret_cast<float*>(p.out) + orow + n0;
-          if constexpr (EPI == EPI_GELU_POS_F32) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = gelu_fast(f[j]);
-          }
-          if (full) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 u = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-              if constexpr (kHasExtra) {
-                const float4 rv = extra[i & 1][j >> 2];
-                u.x += rv.x, u.y += rv.y, u.z += rv.z, u.w += rv.w;
-              }
-              *reinterpret_cast<float4*>(o + j) = u;
-            }
-          } else {
-            const float* xs = (EPI == EPI_GELU_POS_F32) ? p.pos + (long)r * p.N + n0 : o;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.N) o[j] = (kHasExtra ? xs[j] : 0.f) + f[j];
-          }
-        } else if constexpr (EPI == EPI_CROSSKV_BF16) {
-          // n0 is 32-aligned, so the chunk stays inside one (layer, k|v, head) slice of 64 columns
-          const int which = n0 / p.d_model;  // layer * 2 + kv
-          const int within = n0 - which * p.d_model;
-          const int h = within >> 6, dh = within & 63;
-          const int layer = which >> 1;
-          __nv_bfloat16* base = (which & 1) ? p.cross_v : p.cross_k;
-          const long off = ((((long)layer * p.kv_batch + (c.batch + p.kv_batch_offset)) * p.n_head + h) * p.n_ctx_kv + r) * 64 + dh;
-          __nv_bfloat16* o = base + off;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 u;
-            u.x = pack_bf16x2(f[j], f[j + 1]), u.y = pack_bf16x2(f[j + 2], f[j + 3]);
-            u.z = pack_bf16x2(f[j + 4], f[j + 5]), u.w = pack_bf16x2(f[j + 6], f[j + 7]);
-            *reinterpret_cast<uint4*>(o + j) = u;
-          }
-        } else if constexpr (EPI == EPI_ARGMAX) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (n0 + j < p.N && f[j] > best) {  // strict '>' keeps the first maximum (std::max_element, Whisper.cpp:42-45)
-              best = f[j];
-              best_idx = n0 + j;
-            }
-          }
-          if (p.out != nullptr) {
-            float* o = reinterpret_cast<float*>(p.out) + orow + n0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.N) o[j] = f[j];
-          }
-        }
-      }
-      if constexpr (EPI == EPI_ARGMAX) {
-        if (row_ok) {
-          const long pi = ((long)c.batch * p.rows_valid + r) * p.part_ld + c.n_blk * (kEpiWarps / 4) + half;
-          p.part_val[pi] = best;
-          p.part_idx[pi] = best_idx;
-        }
-      }
+      epilogue_tile<BLOCK_N, EPI, kEpiWarps>(p, c, tmem_base + acc_stage * BLOCK_N, s_bias + acc_stage * BLOCK_N, &tmem_full_bar[acc_stage],
+                                             acc_phase, warp - 2, warp & 3, lane);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc_stage]);
