@@ -17,6 +17,13 @@ CASES = [
     (2, 384, 384, 32, 2),
     (5, 51865, 384, 128, 6),     # logits + argmax, N not a multiple of anything
     (20000, 768, 768, 128, 3),   # many tiles per CTA (persistent loop, both accumulator stages, phase wrap)
+    # block_n 512 = the CTA-pair kernel (tcgen05.mma.cta_group::2, 256 x 256 tiles)
+    (256, 256, 64, 512, 2),
+    (300, 200, 192, 512, 2),     # ragged M (odd number of 128-row tiles) and N
+    (1500, 1152, 384, 512, 0),
+    (3000, 384, 1536, 512, 3),
+    (1000, 1536, 384, 512, 1),
+    (48000, 768, 768, 512, 3),   # encoder-sized: many tile pairs per cluster
 ]
 
 

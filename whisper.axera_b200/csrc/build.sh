@@ -7,7 +7,7 @@ NVCC=${NVCC:-nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-fvisibility=hidden -Xcompiler -Wall,-Wno-unused-function"
 mkdir -p obj
 pids=()
-for f in logmel.cu gemm_tcgen05.cu encoder_ops.cu attention_tcgen05.cu decode_ops.cu engine.cu model_abi.cu; do
+for f in logmel.cu gemm_tcgen05.cu gemm2cta_tcgen05.cu encoder_ops.cu attention_tcgen05.cu decode_ops.cu engine.cu model_abi.cu; do
   if [ ! -f obj/${f%.cu}.o ] || [ $f -nt obj/${f%.cu}.o ] || [ -n "$(find . -maxdepth 1 \( -name '*.h' -o -name '*.cuh' -o -name '*.inc' \) -newer obj/${f%.cu}.o)" ] || [ -n "$(find ../../include -name '*.h' -newer obj/${f%.cu}.o)" ]; then
     $NVCC $FLAGS -c $f -o obj/${f%.cu}.o &
     pids+=($!)

@@ -66,7 +66,7 @@ __device__ __forceinline__ void attend_one_query(const float* __restrict__ q_glo
 
   // ---- phase 1: scores ----
   float mx = -INFINITY;
-  constexpr int U = 4;  // independent 16-byte loads in flight per thread (48 registers: 3 CTAs/SM leave room for a GEMM CTA)
+  constexpr int U = 4;  // independent 16-byte loads in flight per thread
   for (int jb = warp * 4; jb < n; jb += NW * 4 * U) {  // warp-uniform bounds: the shuffles below need every lane
     const int j0 = jb + grp;
     uint4 kv[U];
@@ -281,166 +281,35 @@ __global__ void __launch_bounds__(kSelfWarps * 32) self_attention_decode_kernel(
 }
 
 // ---- cross attention ---------------------------------------------------------------------------------------
-// The dominant kernel of the whole path: per step and layer every (sequence, head) streams its 1500 x 64 bf16 keys and
-// values (384 KB) exactly once.  Persistent, ONE CTA per SM: a producer thread keeps a 6-stage ring of 16 KB tiles
-// (128 keys) in flight with bulk async copies (cp.async.bulk + mbarrier complete_tx), so ~96 KB per SM are outstanding
-// without holding any registers; 8 consumer warps read the tiles from shared memory (8 lanes x 16 B per key, conflict
-// free), keep the scores of the item in smem, do the fp32 softmax and accumulate P.V.  One CTA of 288 threads / ~48
-// registers / ~107 KB smem per SM leaves room for the small kernels of the OTHER micro-batch, which the engine runs
-// concurrently on a second stream (their latency hides under this HBM-bound stream).
-constexpr int kCrossConsumers = 256;
-constexpr int kCrossThreads = kCrossConsumers + 32;
-constexpr int kCrossStages = 6;
-constexpr int kCrossTileKeys = 128;
-constexpr int kCrossTileBytes = kCrossTileKeys * 128;
-struct CrossSmem {
-  unsigned char ring[kCrossStages][kCrossTileBytes];
-  float scores[1536];
-  float acc[kCrossConsumers / 32][64];
-  float red[kCrossConsumers / 32];
-  float red2[kCrossConsumers / 32];
-  uint64_t full[kCrossStages], empty[kCrossStages];
-};
-
-__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gsrc),
-               "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 2, %0;" ::"n"(kCrossConsumers) : "memory"); }
-
-__global__ void __launch_bounds__(kCrossThreads, 1) cross_attention_decode_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ k,
-                                                                                 const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ out,
-                                                                                 int n_items, int n_head, int T, int n_split, float* __restrict__ part_m,
-                                                                                 float* __restrict__ part_l, float* __restrict__ part_o) {
-  extern __shared__ __align__(128) unsigned char cross_smem_raw[];
-  CrossSmem& S = *reinterpret_cast<CrossSmem*>(cross_smem_raw);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid == 0) {
-    for (int i = 0; i < kCrossStages; ++i) mbar_init(&S.full[i], 1), mbar_init(&S.empty[i], kCrossConsumers / 32);
-    fence_barrier_init();
-  }
-  __syncthreads();
+constexpr int kCrossThreads = 256;
+__global__ void __launch_bounds__(kCrossThreads) cross_attention_decode_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ k,
+                                                                              const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ out,
+                                                                              int n_head, int T, int n_split, float* __restrict__ part_m,
+                                                                              float* __restrict__ part_l, float* __restrict__ part_o) {
+  __shared__ float s_scores[kCrossThreads / 32 * 64 > 1504 ? kCrossThreads / 32 * 64 : 1504];
+  __shared__ float s_red[kCrossThreads / 32];
+  __shared__ float s_out[64];
+  __shared__ float s_ml[2];
   pdl_wait();
+  const int h = blockIdx.x / n_split, sp = blockIdx.x % n_split;
+  const int b = blockIdx.y;
   const int d = n_head * 64;
+  const long kv_off = ((long)b * n_head + h) * T * 64;
   const int per = (T + n_split - 1) / n_split;
-
-  if (warp == kCrossConsumers / 32) {
-    // ===== producer: one thread streams K tiles then V tiles of every item of this CTA through the ring =====
-    if (lane == 0) {
-      int idx = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int sp = item % n_split, bh = item / n_split;
-        const int k_begin = sp * per, k_end = min(T, k_begin + per);
-        const int n = k_end - k_begin, n_chunks = (n + kCrossTileKeys - 1) / kCrossTileKeys;
-        for (int kv = 0; kv < 2; ++kv) {
-          const __nv_bfloat16* src = (kv == 0 ? k : v) + ((long)bh * T + k_begin) * 64;
-          for (int c = 0; c < n_chunks; ++c, ++idx) {
-            const int stage = idx % kCrossStages;
-            const uint32_t bytes = (uint32_t)min(kCrossTileKeys, n - c * kCrossTileKeys) * 128u;
-            mbar_wait(&S.empty[stage], ((idx / kCrossStages) & 1) ^ 1);
-            mbar_arrive_expect_tx(&S.full[stage], bytes);
-            bulk_copy_g2s(S.ring[stage], src + (long)c * kCrossTileKeys * 64, bytes, &S.full[stage]);
-          }
-        }
-      }
-    }
+  const int k_begin = sp * per, k_end = min(T, k_begin + per);
+  attend_one_query<kCrossThreads>(q + (long)b * d + h * 64, k + kv_off, v + kv_off, k_begin, k_end, nullptr, nullptr, s_scores, s_red,
+                                  s_out, s_ml);
+  pdl_launch_dependents();  // multi-wave kernel: let the successor start only in this CTA's tail
+  if (n_split == 1) {
+    if (threadIdx.x < 64) out[(long)b * d + h * 64 + threadIdx.x] = __float2bfloat16_rn(s_out[threadIdx.x] / s_ml[1]);
   } else {
-    // ===== consumers =====
-    const int grp = lane >> 3, sub = lane & 7;
-    int idx = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int sp = item % n_split, bh = item / n_split;
-      const int b = bh / n_head, h = bh - b * n_head;
-      const int k_begin = sp * per, k_end = min(T, k_begin + per);
-      const int n = k_end - k_begin, n_chunks = (n + kCrossTileKeys - 1) / kCrossTileKeys;
-      float qv[8];
-      {
-        const float* qg = q + (long)b * d + h * 64 + sub * 8;
-        const float4 a = *reinterpret_cast<const float4*>(qg), c = *reinterpret_cast<const float4*>(qg + 4);
-        qv[0] = a.x, qv[1] = a.y, qv[2] = a.z, qv[3] = a.w, qv[4] = c.x, qv[5] = c.y, qv[6] = c.z, qv[7] = c.w;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) qv[i] *= kScoreScaleLog2;
-      }
-      // ---- scores ----
-      float mx = -INFINITY;
-      for (int c = 0; c < n_chunks; ++c, ++idx) {
-        const int stage = idx % kCrossStages;
-        const int nk = min(kCrossTileKeys, n - c * kCrossTileKeys);
-        mbar_wait(&S.full[stage], (idx / kCrossStages) & 1);
-        const uint4* tile = reinterpret_cast<const uint4*>(S.ring[stage]);
-#pragma unroll
-        for (int it = 0; it < kCrossTileKeys / 32; ++it) {
-          const int j = it * 32 + warp * 4 + grp;  // key within the tile
-          const uint4 kk = j < nk ? tile[j * 8 + sub] : make_uint4(0, 0, 0, 0);
-          float sc = dot8(kk, qv);
-          sc += __shfl_xor_sync(0xffffffffu, sc, 1);
-          sc += __shfl_xor_sync(0xffffffffu, sc, 2);
-          sc += __shfl_xor_sync(0xffffffffu, sc, 4);
-          if (j < nk) {
-            if (sub == 0) S.scores[c * kCrossTileKeys + j] = sc;
-            mx = fmaxf(mx, sc);
-          }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&S.empty[stage]);
-      }
-      mx = warp_max(mx);
-      if (lane == 0) S.red[warp] = mx;
-      consumer_sync();  // also publishes S.scores
-      float m = S.red[0];
-#pragma unroll
-      for (int w = 1; w < kCrossConsumers / 32; ++w) m = fmaxf(m, S.red[w]);
-      // ---- softmax weights and P.V ----
-      float acc[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-      float lsum = 0.f;
-      for (int c = 0; c < n_chunks; ++c, ++idx) {
-        const int stage = idx % kCrossStages;
-        const int nk = min(kCrossTileKeys, n - c * kCrossTileKeys);
-        mbar_wait(&S.full[stage], (idx / kCrossStages) & 1);
-        const uint4* tile = reinterpret_cast<const uint4*>(S.ring[stage]);
-#pragma unroll
-        for (int it = 0; it < kCrossTileKeys / 32; ++it) {
-          const int j = it * 32 + warp * 4 + grp;
-          if (j < nk) {
-            const float pw = exp2f(S.scores[c * kCrossTileKeys + j] - m);
-            axpy8(acc, pw, tile[j * 8 + sub]);
-            if (sub == 0) lsum += pw;
-          }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&S.empty[stage]);
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
-        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
-      }
-      lsum = warp_sum(lsum);
-      if (grp == 0) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) S.acc[warp][sub * 8 + i] = acc[i];
-      }
-      if (lane == 0) S.red2[warp] = lsum;
-      consumer_sync();
-      if (tid < 64) {
-        float o = 0.f, l = 0.f;
-#pragma unroll
-        for (int w = 0; w < kCrossConsumers / 32; ++w) o += S.acc[w][tid], l += S.red2[w];
-        if (n_split == 1) {
-          out[(long)b * d + h * 64 + tid] = __float2bfloat16_rn(o / l);
-        } else {
-          const long pi = (long)bh * n_split + sp;
-          part_o[pi * 64 + tid] = o;
-          if (tid == 0) part_m[pi] = m, part_l[pi] = l;
-        }
-      }
-      consumer_sync();  // scores / acc / red are rewritten by the next item
+    const long pi = ((long)b * n_head + h) * n_split + sp;
+    if (threadIdx.x < 64) part_o[pi * 64 + threadIdx.x] = s_out[threadIdx.x];
+    if (threadIdx.x == 0) {
+      part_m[pi] = s_ml[0];
+      part_l[pi] = s_ml[1];
     }
   }
-  pdl_launch_dependents();
 }
 
 __global__ void cross_attention_combine_kernel(const float* __restrict__ part_m, const float* __restrict__ part_l,
@@ -522,24 +391,20 @@ void launch_self_attention_decode(const float* qkv, __nv_bfloat16* k_cache, __nv
 }
 
 int cross_attention_pick_split(int B, int n_head) {
-  // one persistent CTA per SM: split the 1500 keys of a (sequence, head) only while there are fewer items than SMs
+  // enough CTAs for ~4 per SM; a single split once the batch provides them
   int split = 1;
-  while (B * n_head * split < kNumSMs && split < 8) split *= 2;
+  while (B * n_head * split < 4 * kNumSMs && split < 8) split *= 2;
   return split;
-}
-
-void decode_ops_set_attributes() {
-  CUDA_CHECK(cudaFuncSetAttribute(cross_attention_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CrossSmem)));
 }
 
 void launch_cross_attention_decode(const float* q, const __nv_bfloat16* k, const __nv_bfloat16* v, __nv_bfloat16* out, int B, int n_head,
                                    int T, int n_split, float* part_m, float* part_l, float* part_o, cudaStream_t stream, bool pdl) {
-  const int n_items = B * n_head * n_split;
-  const int grid = n_items < kNumSMs ? n_items : kNumSMs;
-  launch_k(pdl, cross_attention_decode_kernel, dim3(grid), dim3(kCrossThreads), sizeof(CrossSmem), stream, q, k, v, out, n_items, n_head, T, n_split,
-           part_m, part_l, part_o);
+  dim3 grid(n_head * n_split, B);
+  launch_k(pdl, cross_attention_decode_kernel, grid, dim3(kCrossThreads), 0, stream, q, k, v, out, n_head, T, n_split, part_m, part_l, part_o);
   if (n_split > 1) launch_pdl(cross_attention_combine_kernel, dim3(n_head, B), dim3(64), 0, stream, part_m, part_l, part_o, out, n_head, n_split);
 }
+
+void decode_ops_set_attributes() {}
 
 void launch_argmax_finalize(const DecodeState& st, const float* part_val, const int* part_idx, int n_tiles, int part_ld, int B,
                             int n_text_ctx, int eot, int honor_eot, int sot_len, cudaStream_t stream) {

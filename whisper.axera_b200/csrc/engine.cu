@@ -391,6 +391,7 @@ void Engine::ensure_capacity(int B, long max_samples) {
 
 void Engine::build_plans() {
   const int d = cfg_.d, n_mels = cfg_.n_mels;
+  const bool two = getenv("B200W_GEMM_1CTA") == nullptr;  // encoder GEMMs: CTA-pair kernel (bring-up switch to the 1-CTA kernel)
   auto keep = [&](GemmPlan* p) {
     plans_.push_back(p);
     return p;
@@ -406,7 +407,7 @@ void Engine::build_plans() {
     a.batch_pitch = (long)(kMelFrames + 2) * n_mels;
     a.n_taps = 3, a.k_per_tap = n_mels;
     for (int t = 0; t < 3; ++t) a.tap_c0[t] = 0, a.tap_row[t] = t;
-    p_conv1_ = keep(gemm_plan_create(a, w_conv1_, d, 128, EPI_BIAS_GELU_BF16));
+    p_conv1_ = keep(gemm_plan_create(a, w_conv1_, d, 128, EPI_BIAS_GELU_BF16, two));
   }
   {  // conv2 (stride 2): conv1_out viewed as [sub][1501][2d]; out t reads padded rows 2t, 2t+1, 2t+2
     GemmOperandA a{};
@@ -416,21 +417,21 @@ void Engine::build_plans() {
     a.tap_c0[0] = 0, a.tap_row[0] = 0;
     a.tap_c0[1] = d, a.tap_row[1] = 0;
     a.tap_c0[2] = 0, a.tap_row[2] = 1;
-    p_conv2_ = keep(gemm_plan_create(a, w_conv2_, d, 128, EPI_GELU_POS_F32));
+    p_conv2_ = keep(gemm_plan_create(a, w_conv2_, d, 128, EPI_GELU_POS_F32, two));
   }
   const int rows_sub = enc_sub_ * kAudioCtx;
   enc_plans_.resize(cfg_.l_enc);
   for (int i = 0; i < cfg_.l_enc; ++i) {
     const LayerEnc& L = enc_[i];
-    enc_plans_[i].qkv = keep(gemm_plan_create(flat(h_enc_, d, rows_sub), L.w_qkv, 3 * d, 256, EPI_BIAS_BF16));
-    enc_plans_[i].out = keep(gemm_plan_create(flat(attn_enc_, d, rows_sub), L.w_out, d, 128, EPI_BIAS_RESID_F32));
-    enc_plans_[i].fc1 = keep(gemm_plan_create(flat(h_enc_, d, rows_sub), L.w_fc1, 4 * d, 256, EPI_BIAS_GELU_BF16));
-    enc_plans_[i].fc2 = keep(gemm_plan_create(flat(mlp_enc_, 4 * d, rows_sub), L.w_fc2, d, 128, EPI_BIAS_RESID_F32));
+    enc_plans_[i].qkv = keep(gemm_plan_create(flat(h_enc_, d, rows_sub), L.w_qkv, 3 * d, 256, EPI_BIAS_BF16, two));
+    enc_plans_[i].out = keep(gemm_plan_create(flat(attn_enc_, d, rows_sub), L.w_out, d, 128, EPI_BIAS_RESID_F32, two));
+    enc_plans_[i].fc1 = keep(gemm_plan_create(flat(h_enc_, d, rows_sub), L.w_fc1, 4 * d, 256, EPI_BIAS_GELU_BF16, two));
+    enc_plans_[i].fc2 = keep(gemm_plan_create(flat(mlp_enc_, 4 * d, rows_sub), L.w_fc2, d, 128, EPI_BIAS_RESID_F32, two));
   }
   {  // cross K/V: rows are (chunk, t) so the epilogue can scatter head-major per chunk
     GemmOperandA a{};
     a.ptr = h_enc_, a.K = d, a.rows = kAudioCtx, a.n_batch = enc_sub_, a.row_pitch = d, a.batch_pitch = (long)kAudioCtx * d, a.n_taps = 0;
-    p_crosskv_ = keep(gemm_plan_create(a, w_crosskv_, 2 * cfg_.l_dec * d, 256, EPI_CROSSKV_BF16));
+    p_crosskv_ = keep(gemm_plan_create(a, w_crosskv_, 2 * cfg_.l_dec * d, 256, EPI_CROSSKV_BF16, two));
   }
   dec_plans_.resize(cfg_.l_dec);
   const int bn = 64;

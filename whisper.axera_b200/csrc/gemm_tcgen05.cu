@@ -27,6 +27,10 @@ namespace b200w {
 
 using namespace gemm_detail;
 
+void gemm2cta_launch(const CUtensorMap& ta, const CUtensorMap& tb, int epilogue, int n_batch, int n_taps, int kb_per_tap, const int* a_c0,
+                     const int* a_row, const int* w_k0, const GemmParams& p, cudaStream_t stream);
+void gemm2cta_set_attributes();
+
 namespace {
 
 constexpr int kSmemBudget = 196608;  // 192 KB of operand stages
@@ -36,9 +40,7 @@ struct GemmCfg {
   static constexpr int kStageBytesA = BLOCK_M * BLOCK_K * 2;
   static constexpr int kStageBytesB = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-  // the narrow tiles are the decoder-step GEMMs: they co-reside with the cross-attention CTAs of the other micro-batch,
-  // so they take less shared memory (6-7 stages) and fewer registers / threads
-  static constexpr int kStages = (BLOCK_N >= 128 ? kSmemBudget : 98304) / kStageBytes;  // 256 -> 4, 128 -> 6, 64 -> 4, 32 -> 4
+  static constexpr int kStages = kSmemBudget / kStageBytes;  // 256 -> 4, 128 -> 6, 64 -> 8, 32 -> 9
   static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
   static constexpr int kEpiWarps = BLOCK_N >= 128 ? 8 : 4;  // 8: two warps per TMEM lane group, each taking half of the columns
   static constexpr int kMinCtas = BLOCK_N >= 128 ? 1 : 2;    // register cap (<= 168) for the narrow tiles
@@ -270,6 +272,7 @@ void set_attr_epi() {
 }  // namespace
 
 void gemm_set_attributes() {
+  gemm2cta_set_attributes();
   set_attr_epi<EPI_BIAS_BF16>();
   set_attr_epi<EPI_BIAS_GELU_BF16>();
   set_attr_epi<EPI_BIAS_F32>();
@@ -283,9 +286,12 @@ struct GemmPlan {
   CUtensorMap tmap_a, tmap_b;
   GemmGeom geom;
   int block_n, epilogue, grid;
+  bool two_cta;
 };
 
-GemmPlan* gemm_plan_create(const GemmOperandA& a, const __nv_bfloat16* w, int n_rows_w, int block_n, int epilogue) {
+
+
+GemmPlan* gemm_plan_create(const GemmOperandA& a, const __nv_bfloat16* w, int n_rows_w, int block_n, int epilogue, bool two_cta) {
   if ((a.row_pitch * 2) % 16 != 0 || (a.batch_pitch * 2) % 16 != 0) throw CudaError("gemm: operand pitches must be multiples of 16 bytes");
   GemmPlan* pl = new GemmPlan();
   const uint64_t adims[3] = {(uint64_t)a.K, (uint64_t)a.rows, (uint64_t)a.n_batch};
@@ -298,10 +304,12 @@ GemmPlan* gemm_plan_create(const GemmOperandA& a, const __nv_bfloat16* w, int n_
   if ((w_k * 2) % 16 != 0) throw CudaError("gemm: weight row pitch must be a multiple of 16 bytes");
   const uint64_t bdims[2] = {(uint64_t)w_k, (uint64_t)n_rows_w};
   const uint64_t bpitch[1] = {(uint64_t)w_k * 2};
-  const uint32_t bbox[2] = {BLOCK_K, (uint32_t)block_n};
+  if (two_cta) block_n = 256;  // pair tile 256 x 256; each CTA of the pair stages 128 rows of W
+  const uint32_t bbox[2] = {BLOCK_K, (uint32_t)(two_cta ? 128 : block_n)};
   pl->tmap_b = make_tmap(w, 2, bdims, bpitch, bbox);
   pl->block_n = block_n;
   pl->epilogue = epilogue;
+  pl->two_cta = two_cta;
   pl->geom.n_batch = a.n_batch;
   pl->geom.n_taps = n_taps;
   pl->geom.kb_per_tap = (k_per_tap + BLOCK_K - 1) / BLOCK_K;
@@ -319,6 +327,11 @@ GemmPlan* gemm_plan_create(const GemmOperandA& a, const __nv_bfloat16* w, int n_
 void gemm_plan_destroy(GemmPlan* p) { delete p; }
 
 void gemm_launch(const GemmPlan* plan, const GemmParams& p, cudaStream_t stream) {
+  if (plan->two_cta) {
+    gemm2cta_launch(plan->tmap_a, plan->tmap_b, plan->epilogue, plan->geom.n_batch, plan->geom.n_taps, plan->geom.kb_per_tap, plan->geom.a_c0,
+                    plan->geom.a_row, plan->geom.w_k0, p, stream);
+    return;
+  }
   GemmGeom g = plan->geom;
   g.m_tiles_per_batch = (p.rows_valid + BLOCK_M - 1) / BLOCK_M;
   g.n_tiles = (p.N + plan->block_n - 1) / plan->block_n;

@@ -85,7 +85,8 @@ struct GemmParams {
 };
 
 struct GemmPlan;  // opaque: tensor maps + launch geometry, built once per (operand, shape)
-GemmPlan* gemm_plan_create(const GemmOperandA& a, const __nv_bfloat16* w, int n_rows_w, int block_n, int epilogue);
+// two_cta: 256 x 256 tiles computed by CTA pairs (tcgen05.mma.cta_group::2, gemm2cta_tcgen05.cu); for the large-M encoder GEMMs
+GemmPlan* gemm_plan_create(const GemmOperandA& a, const __nv_bfloat16* w, int n_rows_w, int block_n, int epilogue, bool two_cta = false);
 void gemm_plan_destroy(GemmPlan*);
 void gemm_launch(const GemmPlan* plan, const GemmParams& p, cudaStream_t stream);
 // plain SIMT comparator used by the self-tests only (same operand conventions, f32 output = acc + bias)

@@ -336,7 +336,7 @@ int b200w_selftest_gemm(int M, int N, int K, int block_n, int epilogue, unsigned
     gemm_set_attributes();
     std::mt19937 rng(seed);
     std::normal_distribution<float> nd(0.f, 1.f);
-    const int Mpad = (M + 127) / 128 * 128, Npad = (N + 255) / 256 * 256;
+    const int Mpad = (M + 255) / 256 * 256, Npad = (N + 255) / 256 * 256;
     std::vector<__nv_bfloat16> ha((size_t)Mpad * K), hw((size_t)Npad * K);
     for (auto& v : ha) v = __float2bfloat16(0.f);
     for (auto& v : hw) v = __float2bfloat16(0.f);
@@ -369,7 +369,8 @@ int b200w_selftest_gemm(int M, int N, int K, int block_n, int epilogue, unsigned
     gemm_reference_simt(da, K, dw, K, db, dref, N, M, N, K, s);
     GemmOperandA a{};
     a.ptr = da, a.K = K, a.rows = Mpad, a.n_batch = 1, a.row_pitch = K, a.batch_pitch = (long)Mpad * K, a.n_taps = 0;
-    GemmPlan* plan = gemm_plan_create(a, dw, Npad, block_n, epilogue);
+    const bool two_cta = block_n == 512;  // test-hook convention: block_n 512 selects the CTA-pair kernel (256 x 256 tiles)
+    GemmPlan* plan = gemm_plan_create(a, dw, Npad, two_cta ? 256 : block_n, epilogue, two_cta);
     GemmParams p{};
     p.rows_valid = M, p.N = N, p.ldo = N, p.bias = db, p.n_batch = 1;
     const bool bf_out = epilogue == EPI_BIAS_BF16 || epilogue == EPI_BIAS_GELU_BF16;
