@@ -392,6 +392,7 @@ void Engine::ensure_capacity(int B, long max_samples) {
 void Engine::build_plans() {
   const int d = cfg_.d, n_mels = cfg_.n_mels;
   const bool two = getenv("B200W_GEMM_1CTA") == nullptr;  // encoder GEMMs: CTA-pair kernel (bring-up switch to the 1-CTA kernel)
+  const bool tma_out = two && getenv("B200W_GEMM_DIRECT_STORE") == nullptr;  // epilogues through TMA stores / reduce-adds
   auto keep = [&](GemmPlan* p) {
     plans_.push_back(p);
     return p;
@@ -423,15 +424,18 @@ void Engine::build_plans() {
   enc_plans_.resize(cfg_.l_enc);
   for (int i = 0; i < cfg_.l_enc; ++i) {
     const LayerEnc& L = enc_[i];
-    enc_plans_[i].qkv = keep(gemm_plan_create(flat(h_enc_, d, rows_sub), L.w_qkv, 3 * d, 256, EPI_BIAS_BF16, two));
-    enc_plans_[i].out = keep(gemm_plan_create(flat(attn_enc_, d, rows_sub), L.w_out, d, 128, EPI_BIAS_RESID_F32, two));
-    enc_plans_[i].fc1 = keep(gemm_plan_create(flat(h_enc_, d, rows_sub), L.w_fc1, 4 * d, 256, EPI_BIAS_GELU_BF16, two));
-    enc_plans_[i].fc2 = keep(gemm_plan_create(flat(mlp_enc_, 4 * d, rows_sub), L.w_fc2, d, 128, EPI_BIAS_RESID_F32, two));
+    const GemmTmaOut o_qkv{qkv_enc_, nullptr, rows_sub, 3L * d, 3L * d, 0}, o_x{x_enc_, nullptr, rows_sub, d, d, 0};
+    const GemmTmaOut o_mlp{mlp_enc_, nullptr, rows_sub, 4L * d, 4L * d, 0};
+    enc_plans_[i].qkv = keep(gemm_plan_create(flat(h_enc_, d, rows_sub), L.w_qkv, 3 * d, 256, EPI_BIAS_BF16, two, tma_out ? &o_qkv : nullptr));
+    enc_plans_[i].out = keep(gemm_plan_create(flat(attn_enc_, d, rows_sub), L.w_out, d, 128, EPI_BIAS_RESID_F32, two, tma_out ? &o_x : nullptr));
+    enc_plans_[i].fc1 = keep(gemm_plan_create(flat(h_enc_, d, rows_sub), L.w_fc1, 4 * d, 256, EPI_BIAS_GELU_BF16, two, tma_out ? &o_mlp : nullptr));
+    enc_plans_[i].fc2 = keep(gemm_plan_create(flat(mlp_enc_, 4 * d, rows_sub), L.w_fc2, d, 128, EPI_BIAS_RESID_F32, two, tma_out ? &o_x : nullptr));
   }
   {  // cross K/V: rows are (chunk, t) so the epilogue can scatter head-major per chunk
     GemmOperandA a{};
     a.ptr = h_enc_, a.K = d, a.rows = kAudioCtx, a.n_batch = enc_sub_, a.row_pitch = d, a.batch_pitch = (long)kAudioCtx * d, a.n_taps = 0;
-    p_crosskv_ = keep(gemm_plan_create(a, w_crosskv_, 2 * cfg_.l_dec * d, 256, EPI_CROSSKV_BF16, two));
+    const GemmTmaOut o_kv{cross_k_, cross_v_, kAudioCtx, 64, 64, (long)cfg_.l_dec * cap_ * cfg_.n_head};
+    p_crosskv_ = keep(gemm_plan_create(a, w_crosskv_, 2 * cfg_.l_dec * d, 256, EPI_CROSSKV_BF16, two, tma_out ? &o_kv : nullptr));
   }
   dec_plans_.resize(cfg_.l_dec);
   const int bn = 64;

@@ -27,8 +27,8 @@ namespace b200w {
 
 using namespace gemm_detail;
 
-void gemm2cta_launch(const CUtensorMap& ta, const CUtensorMap& tb, int epilogue, int n_batch, int n_taps, int kb_per_tap, const int* a_c0,
-                     const int* a_row, const int* w_k0, const GemmParams& p, cudaStream_t stream);
+void gemm2cta_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* to, const CUtensorMap* to2, int epilogue, int n_batch,
+                     int n_taps, int kb_per_tap, const int* a_c0, const int* a_row, const int* w_k0, const GemmParams& p, cudaStream_t stream);
 void gemm2cta_set_attributes();
 
 namespace {
@@ -207,7 +207,11 @@ PFN_encodeTiled get_encode_fn() {
 
 }  // namespace
 
+CUtensorMap make_tmap_sw128(const void* base, bool f32, int rank, const uint64_t* dims, const uint64_t* pitches_bytes, const uint32_t* box);
 CUtensorMap make_tmap_bf16_sw128(const void* base, int rank, const uint64_t* dims, const uint64_t* pitches_bytes, const uint32_t* box) {
+  return make_tmap_sw128(base, false, rank, dims, pitches_bytes, box);
+}
+CUtensorMap make_tmap_sw128(const void* base, bool f32, int rank, const uint64_t* dims, const uint64_t* pitches_bytes, const uint32_t* box) {
   CUtensorMap m;
   cuuint64_t gdim[3], gstr[2];
   cuuint32_t bdim[3], estr[3];
@@ -217,7 +221,7 @@ CUtensorMap make_tmap_bf16_sw128(const void* base, int rank, const uint64_t* dim
     estr[i] = 1;
   }
   for (int i = 0; i < rank - 1; ++i) gstr[i] = pitches_bytes[i];
-  CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
+  CUresult r = get_encode_fn()(&m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -287,11 +291,14 @@ struct GemmPlan {
   GemmGeom geom;
   int block_n, epilogue, grid;
   bool two_cta;
+  bool has_out;            // two_cta only: outputs leave through TMA stores / reduce-adds
+  CUtensorMap tmap_out, tmap_out2;
 };
 
 
 
-GemmPlan* gemm_plan_create(const GemmOperandA& a, const __nv_bfloat16* w, int n_rows_w, int block_n, int epilogue, bool two_cta) {
+GemmPlan* gemm_plan_create(const GemmOperandA& a, const __nv_bfloat16* w, int n_rows_w, int block_n, int epilogue, bool two_cta,
+                           const GemmTmaOut* out) {
   if ((a.row_pitch * 2) % 16 != 0 || (a.batch_pitch * 2) % 16 != 0) throw CudaError("gemm: operand pitches must be multiples of 16 bytes");
   GemmPlan* pl = new GemmPlan();
   const uint64_t adims[3] = {(uint64_t)a.K, (uint64_t)a.rows, (uint64_t)a.n_batch};
@@ -310,6 +317,25 @@ GemmPlan* gemm_plan_create(const GemmOperandA& a, const __nv_bfloat16* w, int n_
   pl->block_n = block_n;
   pl->epilogue = epilogue;
   pl->two_cta = two_cta;
+  pl->has_out = false;
+  if (two_cta && out != nullptr) {
+    pl->has_out = true;
+    if (epilogue == EPI_CROSSKV_BF16) {
+      // cross K / V [L*B*H][T][64] bf16: one 64-column box = one head; rows past T are clipped by TMA
+      const uint64_t od[3] = {64, (uint64_t)out->rows, (uint64_t)out->n_slices};
+      const uint64_t op[2] = {128, (uint64_t)out->rows * 128};
+      const uint32_t ob[3] = {64, 128, 1};
+      pl->tmap_out = make_tmap_sw128(out->ptr, false, 3, od, op, ob);
+      pl->tmap_out2 = make_tmap_sw128(out->ptr2, false, 3, od, op, ob);
+    } else {
+      const bool f32 = epilogue == EPI_BIAS_RESID_F32;
+      const uint64_t od[2] = {(uint64_t)out->cols, (uint64_t)out->rows};
+      const uint64_t op[1] = {(uint64_t)out->ld * (f32 ? 4 : 2)};
+      const uint32_t ob[2] = {f32 ? 32u : 64u, 128};
+      pl->tmap_out = make_tmap_sw128(out->ptr, f32, 2, od, op, ob);
+      pl->tmap_out2 = pl->tmap_out;
+    }
+  }
   pl->geom.n_batch = a.n_batch;
   pl->geom.n_taps = n_taps;
   pl->geom.kb_per_tap = (k_per_tap + BLOCK_K - 1) / BLOCK_K;
@@ -328,8 +354,9 @@ void gemm_plan_destroy(GemmPlan* p) { delete p; }
 
 void gemm_launch(const GemmPlan* plan, const GemmParams& p, cudaStream_t stream) {
   if (plan->two_cta) {
-    gemm2cta_launch(plan->tmap_a, plan->tmap_b, plan->epilogue, plan->geom.n_batch, plan->geom.n_taps, plan->geom.kb_per_tap, plan->geom.a_c0,
-                    plan->geom.a_row, plan->geom.w_k0, p, stream);
+    gemm2cta_launch(plan->tmap_a, plan->tmap_b, plan->has_out ? &plan->tmap_out : nullptr, plan->has_out ? &plan->tmap_out2 : nullptr,
+                    plan->epilogue, plan->geom.n_batch, plan->geom.n_taps, plan->geom.kb_per_tap, plan->geom.a_c0, plan->geom.a_row,
+                    plan->geom.w_k0, p, stream);
     return;
   }
   GemmGeom g = plan->geom;

@@ -85,8 +85,17 @@ struct GemmParams {
 };
 
 struct GemmPlan;  // opaque: tensor maps + launch geometry, built once per (operand, shape)
+// Output tensor of a two-CTA GEMM whose epilogue leaves through TMA (plain [rows][cols] tensor; for EPI_CROSSKV_BF16 the two
+// head-major caches viewed as [n_slices][rows = T][64]).
+struct GemmTmaOut {
+  void* ptr;
+  void* ptr2;
+  long rows, cols, ld;
+  long n_slices;
+};
 // two_cta: 256 x 256 tiles computed by CTA pairs (tcgen05.mma.cta_group::2, gemm2cta_tcgen05.cu); for the large-M encoder GEMMs
-GemmPlan* gemm_plan_create(const GemmOperandA& a, const __nv_bfloat16* w, int n_rows_w, int block_n, int epilogue, bool two_cta = false);
+GemmPlan* gemm_plan_create(const GemmOperandA& a, const __nv_bfloat16* w, int n_rows_w, int block_n, int epilogue, bool two_cta = false,
+                           const GemmTmaOut* out = nullptr);
 void gemm_plan_destroy(GemmPlan*);
 void gemm_launch(const GemmPlan* plan, const GemmParams& p, cudaStream_t stream);
 // plain SIMT comparator used by the self-tests only (same operand conventions, f32 output = acc + bias)
