@@ -174,12 +174,16 @@ encoder_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, con
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar.s_free[sb]);  // S_j is in registers: the tensor core may overwrite the buffer
       const int nvalid = T - j * kKV;               // keys of this tile that exist (>= 64 except for the last tile)
+      if (nvalid < kKV) {                           // last tile only: mask the keys past T (warp-uniform branch)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (i >= nvalid) s0[i] = 0xff800000u;     // -inf
+          if (i + 32 >= nvalid) s1[i] = 0xff800000u;
+        }
+      }
       float mx = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        if (i < nvalid) mx = fmaxf(mx, __uint_as_float(s0[i]));
-        if (i + 32 < nvalid) mx = fmaxf(mx, __uint_as_float(s1[i]));
-      }
+      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(s0[i]), __uint_as_float(s1[i])));
       const float m_new = fmaxf(m_run, mx);
       const float alpha = fast_exp2((m_run - m_new) * kScaleLog2);
       const float msc = m_new * kScaleLog2;
@@ -187,10 +191,10 @@ encoder_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, con
       uint32_t pk[32];
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
-        const float a0 = i < nvalid ? fast_exp2(fmaf(__uint_as_float(s0[i]), kScaleLog2, -msc)) : 0.f;
-        const float a1 = i + 1 < nvalid ? fast_exp2(fmaf(__uint_as_float(s0[i + 1]), kScaleLog2, -msc)) : 0.f;
-        const float b0 = i + 32 < nvalid ? fast_exp2(fmaf(__uint_as_float(s1[i]), kScaleLog2, -msc)) : 0.f;
-        const float b1 = i + 33 < nvalid ? fast_exp2(fmaf(__uint_as_float(s1[i + 1]), kScaleLog2, -msc)) : 0.f;
+        const float a0 = fast_exp2(fmaf(__uint_as_float(s0[i]), kScaleLog2, -msc));  // exp2(-inf) = 0 for masked keys
+        const float a1 = fast_exp2(fmaf(__uint_as_float(s0[i + 1]), kScaleLog2, -msc));
+        const float b0 = fast_exp2(fmaf(__uint_as_float(s1[i]), kScaleLog2, -msc));
+        const float b1 = fast_exp2(fmaf(__uint_as_float(s1[i + 1]), kScaleLog2, -msc));
         rs += (a0 + a1) + (b0 + b1);
         pk[i >> 1] = pack_bf16x2(a0, a1);
         pk[16 + (i >> 1)] = pack_bf16x2(b0, b1);
@@ -217,10 +221,18 @@ encoder_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, con
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar.o_free[ob]);
+        if (__any_sync(0xffffffffu, alpha != 1.0f)) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          o[i] = (o[i] + __uint_as_float(t0[i])) * alpha;
-          o[i + 32] = (o[i + 32] + __uint_as_float(t1[i])) * alpha;
+          for (int i = 0; i < 32; ++i) {
+            o[i] = (o[i] + __uint_as_float(t0[i])) * alpha;
+            o[i + 32] = (o[i + 32] + __uint_as_float(t1[i])) * alpha;
+          }
+        } else {  // the running maximum of every row of this warp is unchanged (the common case after the first tiles)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            o[i] += __uint_as_float(t0[i]);
+            o[i + 32] += __uint_as_float(t1[i]);
+          }
         }
       }
       m_run = m_new;

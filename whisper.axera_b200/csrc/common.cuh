@@ -74,21 +74,26 @@ __device__ __forceinline__ float bf16hi_to_f32(uint32_t v) { return __uint_as_fl
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-// GELU(x) = x * Phi(x) with erf from Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7): 2 MUFU + ~12 FMA per element
-// instead of erff()'s ~40 instructions; the epilogues that use it round to bf16 (or add into an fp32 stream whose
-// consumers round to bf16), so the 1e-7 deviation from the exact-erf GELU of the reference graph is invisible.
+// GELU(x) = x * Phi(x), exact-erf form of the reference graph, evaluated as x * sigmoid(2 h(x)) with
+// h(x) = atanh(erf(x / sqrt 2)) fitted by an odd degree-9 polynomial (max |error| of the fit 5.6e-6 over all x, checked
+// against scipy's erf; the sigmoid form has no cancellation in the negative tail).  8 FP32 ops + 2 MUFU (ex2, rcp) per
+// element instead of ~40 instructions for erff(); every consumer rounds the result to bf16 (2^-9 relative).
 __device__ __forceinline__ float gelu_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  const float e = exp2f(-z * z * 1.4426950408889634f);
-  const float erf_abs = fmaf(-poly, e, 1.0f);
-  const float erf_v = copysignf(erf_abs, x);
-  return 0.5f * x * (1.0f + erf_v);
+  // coefficients of h(x)/x in x^2, pre-multiplied by -2 * log2(e) so that exp(-2 h) = ex2(x * p(x^2))
+  constexpr float k0 = -2.0f * 1.4426950408889634f * 0.79784167f;
+  constexpr float k1 = -2.0f * 1.4426950408889634f * 0.0364277193f;
+  constexpr float k2 = -2.0f * 1.4426950408889634f * -0.00010117167f;
+  constexpr float k3 = -2.0f * 1.4426950408889634f * -3.49055965e-05f;
+  constexpr float k4 = -2.0f * 1.4426950408889634f * 1.35273867e-06f;
+  const float x2 = fminf(x * x, 36.0f);  // the fit covers |x| <= 6; beyond, Phi is 0 or 1 to fp32 precision either way
+  float pz = fmaf(k4, x2, k3);
+  pz = fmaf(pz, x2, k2);
+  pz = fmaf(pz, x2, k1);
+  pz = fmaf(pz, x2, k0);
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * pz));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return x * r;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
