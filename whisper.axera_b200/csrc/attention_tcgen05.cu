@@ -3,16 +3,17 @@
 // Math: MultiHeadAttention.qkv_attention of openai-whisper 20240930 as used by the reference's encoder graph
 // (/root/reference/model_convert/export_onnx.py:153-181): w = softmax((q * s)(k * s)^T) with s = 64^-0.25, out = w v.
 //
-// One CTA = 128 query rows of one (chunk, head); keys/values stream through in 64-key tiles.  192 threads:
+// One CTA = 128 query rows of one (chunk, head); keys/values stream through in 64-key tiles.  320 threads:
 //   warp 0 (1 lane)  TMA producer: Q tile once, then K/V tiles through a 4-slot ring in the order the MMA warp
 //                    consumes them (K0 K1 V0 K2 V1 ...), straight out of the fused QKV activation [B][T][3d] (3-D tensor
 //                    map, SWIZZLE_128B; rows past T are zero-filled by TMA)
 //   warp 1 (1 lane)  MMA issuer: S_j = Q K_j^T (M128 N64 K64, both operands K-major) into one of two TMEM S buffers,
 //                    then PV_j = P_j V_j (A = P from smem K-major, B = V tile as loaded = MN-major) into one of two
 //                    64-column TMEM buffers; tcgen05.commit signals the softmax warps and frees smem slots
-//   warps 2-5        softmax: thread = query row (TMEM lane).  Reads S_j (64 fp32) with tcgen05.ld, online max / exp2 /
-//                    sum in fp32, writes P_j as bf16 into the swizzled K-major smem tile, then folds the previous tile's
-//                    PV product into the fp32 output row it keeps in registers: O = (O + PV_{j-1}) * alpha_j.
+//   warps 2-9        softmax: two threads per query row (TMEM lane), 32 keys and 32 output columns each.  Read S_j with
+//                    tcgen05.ld, online max (halves exchanged through smem) / exp2 / sum in fp32, write P_j as bf16 into
+//                    the swizzled K-major smem tile, then fold the previous tile's PV product into the fp32 output they
+//                    keep in registers: O = (O + PV_{j-1}) * alpha_j (rescale skipped while no maximum changes).
 // S_{j+1} is issued before PV_j, so the tensor core works on the next scores while the softmax warps are in their exp
 // phase; two CTAs are resident per SM (256 TMEM columns and ~82 KB smem each) and interleave as well.
 #include <cfloat>
@@ -26,11 +27,11 @@ namespace {
 constexpr int kQ = 128;
 constexpr int kKV = 64;
 constexpr int kRing = 4;
-constexpr int kAttThreads = 192;
+constexpr int kAttThreads = 320;  // TMA warp, MMA warp, 8 softmax warps
 constexpr int kQBytes = kQ * 64 * 2;         // 16 KB
 constexpr int kKVBytes = kKV * 64 * 2;       // 8 KB
 constexpr int kPBytes = kQ * kKV * 2;        // 16 KB
-constexpr int kSmemBytes = kQBytes + kRing * kKVBytes + 2 * kPBytes + 256 + 1024;
+
 constexpr float kScaleLog2 = 0.125f * 1.4426950408889634f;  // (64^-0.25)^2 * log2(e)
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -57,6 +58,8 @@ struct Bars {
   uint64_t s_full[2], s_free[2], p_ready[2], p_free[2], o_full[2], o_free[2];
   uint32_t tmem_slot;
 };
+constexpr int kXchBytes = 2 * 2 * kQ * 4;  // row-max exchange between the two threads of a row: [tile parity][half][row]
+constexpr int kSmemBytes = kQBytes + kRing * kKVBytes + 2 * kPBytes + 256 + kXchBytes + 1024;
 
 __global__ void __launch_bounds__(kAttThreads, 2)
 encoder_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
@@ -67,6 +70,7 @@ encoder_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, con
   unsigned char* sRing = sQ + kQBytes;
   unsigned char* sP = sRing + kRing * kKVBytes;
   Bars& bar = *reinterpret_cast<Bars*>(sP + 2 * kPBytes);
+  float(*xch)[2][kQ] = reinterpret_cast<float(*)[2][kQ]>(sP + 2 * kPBytes + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kQ, h = blockIdx.y, b = blockIdx.z;
@@ -78,9 +82,9 @@ encoder_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, con
     mbar_init(&bar.q_full, 1);
     for (int i = 0; i < kRing; ++i) mbar_init(&bar.ring_full[i], 1), mbar_init(&bar.ring_free[i], 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bar.s_full[i], 1), mbar_init(&bar.s_free[i], 4);
-      mbar_init(&bar.p_ready[i], 4), mbar_init(&bar.p_free[i], 1);
-      mbar_init(&bar.o_full[i], 1), mbar_init(&bar.o_free[i], 4);
+      mbar_init(&bar.s_full[i], 1), mbar_init(&bar.s_free[i], 8);
+      mbar_init(&bar.p_ready[i], 8), mbar_init(&bar.p_free[i], 1);
+      mbar_init(&bar.o_full[i], 1), mbar_init(&bar.o_free[i], 8);
     }
     fence_barrier_init();
   }
@@ -155,57 +159,58 @@ encoder_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, con
       }
     }
   } else {
+    // 8 softmax warps: two warps share a TMEM lane group (= 32 query rows); each takes 32 of the 64 keys of a tile and
+    // 32 of the 64 output columns, so a row's work is split over two threads (more warps in flight per scheduler)
     const int lg = warp & 3;
+    const int ch = (warp - 2) >> 2;  // column half
     const int row = lg * 32 + lane;
     const uint32_t tlane = tmem_base + (static_cast<uint32_t>(lg * 32) << 16);
     float m_run = -INFINITY, l_run = 0.f;
-    float o[64];
+    float o[32];
 #pragma unroll
-    for (int i = 0; i < 64; ++i) o[i] = 0.f;
+    for (int i = 0; i < 32; ++i) o[i] = 0.f;
     for (int j = 0; j < n_tiles; ++j) {
       const int sb = j & 1;
       mbar_wait(&bar.s_full[sb], (j >> 1) & 1);
       tcgen05_fence_after();
-      uint32_t s0[32], s1[32];
-      tmem_ld_32x32b_x32(tlane + sb * 64, s0);
-      tmem_ld_32x32b_x32(tlane + sb * 64 + 32, s1);
+      uint32_t s0[32];
+      tmem_ld_32x32b_x32(tlane + sb * 64 + ch * 32, s0);
       tcgen05_wait_ld();
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar.s_free[sb]);  // S_j is in registers: the tensor core may overwrite the buffer
-      const int nvalid = T - j * kKV;               // keys of this tile that exist (>= 64 except for the last tile)
-      if (nvalid < kKV) {                           // last tile only: mask the keys past T (warp-uniform branch)
+      const int nvalid = T - j * kKV - ch * 32;     // keys of this half-tile that exist
+      if (nvalid < 32) {                            // last tile only: mask the keys past T (warp-uniform branch)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
+        for (int i = 0; i < 32; ++i)
           if (i >= nvalid) s0[i] = 0xff800000u;     // -inf
-          if (i + 32 >= nvalid) s1[i] = 0xff800000u;
-        }
       }
       float mx = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(s0[i]), __uint_as_float(s1[i])));
+      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(s0[i]));
+      // the row maximum needs the other half's keys: exchange through smem (double-buffered by tile parity)
+      xch[sb][ch][row] = mx;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mx = fmaxf(mx, xch[sb][ch ^ 1][row]);
       const float m_new = fmaxf(m_run, mx);
       const float alpha = fast_exp2((m_run - m_new) * kScaleLog2);
       const float msc = m_new * kScaleLog2;
       float rs = 0.f;
-      uint32_t pk[32];
+      uint32_t pk[16];
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
         const float a0 = fast_exp2(fmaf(__uint_as_float(s0[i]), kScaleLog2, -msc));  // exp2(-inf) = 0 for masked keys
         const float a1 = fast_exp2(fmaf(__uint_as_float(s0[i + 1]), kScaleLog2, -msc));
-        const float b0 = fast_exp2(fmaf(__uint_as_float(s1[i]), kScaleLog2, -msc));
-        const float b1 = fast_exp2(fmaf(__uint_as_float(s1[i + 1]), kScaleLog2, -msc));
-        rs += (a0 + a1) + (b0 + b1);
+        rs += a0 + a1;
         pk[i >> 1] = pack_bf16x2(a0, a1);
-        pk[16 + (i >> 1)] = pack_bf16x2(b0, b1);
       }
       l_run = fmaf(l_run, alpha, rs);
       // P_j -> smem, K-major SWIZZLE_128B: row r at r*128 bytes, 16-byte chunk q (keys 8q..8q+7) at position q ^ (r & 7)
       mbar_wait(&bar.p_free[sb], ((j >> 1) & 1) ^ 1);
       unsigned char* prow = sP + sb * kPBytes + row * 128;
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
-        *reinterpret_cast<uint4*>(prow + ((q ^ (row & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+      for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<uint4*>(prow + (((ch * 4 + q) ^ (row & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar.p_ready[sb]);
@@ -214,25 +219,18 @@ encoder_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, con
         const int ob = (j - 1) & 1;
         mbar_wait(&bar.o_full[ob], ((j - 1) >> 1) & 1);
         tcgen05_fence_after();
-        uint32_t t0[32], t1[32];
-        tmem_ld_32x32b_x32(tlane + 128 + ob * 64, t0);
-        tmem_ld_32x32b_x32(tlane + 128 + ob * 64 + 32, t1);
+        uint32_t t0[32];
+        tmem_ld_32x32b_x32(tlane + 128 + ob * 64 + ch * 32, t0);
         tcgen05_wait_ld();
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar.o_free[ob]);
         if (__any_sync(0xffffffffu, alpha != 1.0f)) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            o[i] = (o[i] + __uint_as_float(t0[i])) * alpha;
-            o[i + 32] = (o[i + 32] + __uint_as_float(t1[i])) * alpha;
-          }
+          for (int i = 0; i < 32; ++i) o[i] = (o[i] + __uint_as_float(t0[i])) * alpha;
         } else {  // the running maximum of every row of this warp is unchanged (the common case after the first tiles)
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            o[i] += __uint_as_float(t0[i]);
-            o[i + 32] += __uint_as_float(t1[i]);
-          }
+          for (int i = 0; i < 32; ++i) o[i] += __uint_as_float(t0[i]);
         }
       }
       m_run = m_new;
@@ -241,26 +239,23 @@ encoder_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, con
       const int ob = (n_tiles - 1) & 1;
       mbar_wait(&bar.o_full[ob], ((n_tiles - 1) >> 1) & 1);
       tcgen05_fence_after();
-      uint32_t t0[32], t1[32];
-      tmem_ld_32x32b_x32(tlane + 128 + ob * 64, t0);
-      tmem_ld_32x32b_x32(tlane + 128 + ob * 64 + 32, t1);
+      uint32_t t0[32];
+      tmem_ld_32x32b_x32(tlane + 128 + ob * 64 + ch * 32, t0);
       tcgen05_wait_ld();
-      const float inv = 1.f / l_run;
+      // the row sum is split over the two threads of the row
+      xch[0][ch][row] = l_run;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float inv = 1.f / (l_run + xch[0][ch ^ 1][row]);
       if (q0 + row < T) {
-        __nv_bfloat16* dst = out + ((long)b * T + q0 + row) * d + h * 64;
+        __nv_bfloat16* dst = out + ((long)b * T + q0 + row) * d + h * 64 + ch * 32;
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
-          uint4 u, w;
+          uint4 u;
           u.x = pack_bf16x2((o[i] + __uint_as_float(t0[i])) * inv, (o[i + 1] + __uint_as_float(t0[i + 1])) * inv);
           u.y = pack_bf16x2((o[i + 2] + __uint_as_float(t0[i + 2])) * inv, (o[i + 3] + __uint_as_float(t0[i + 3])) * inv);
           u.z = pack_bf16x2((o[i + 4] + __uint_as_float(t0[i + 4])) * inv, (o[i + 5] + __uint_as_float(t0[i + 5])) * inv);
           u.w = pack_bf16x2((o[i + 6] + __uint_as_float(t0[i + 6])) * inv, (o[i + 7] + __uint_as_float(t0[i + 7])) * inv);
-          w.x = pack_bf16x2((o[32 + i] + __uint_as_float(t1[i])) * inv, (o[33 + i] + __uint_as_float(t1[i + 1])) * inv);
-          w.y = pack_bf16x2((o[34 + i] + __uint_as_float(t1[i + 2])) * inv, (o[35 + i] + __uint_as_float(t1[i + 3])) * inv);
-          w.z = pack_bf16x2((o[36 + i] + __uint_as_float(t1[i + 4])) * inv, (o[37 + i] + __uint_as_float(t1[i + 5])) * inv);
-          w.w = pack_bf16x2((o[38 + i] + __uint_as_float(t1[i + 6])) * inv, (o[39 + i] + __uint_as_float(t1[i + 7])) * inv);
           *reinterpret_cast<uint4*>(dst + i) = u;
-          *reinterpret_cast<uint4*>(dst + 32 + i) = w;
         }
       }
     }
