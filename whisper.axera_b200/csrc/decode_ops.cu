@@ -53,7 +53,7 @@ constexpr float kScoreScaleLog2 = 0.125f * 1.4426950408889634f;  // (64^-0.25)^2
 // (fp32 k1/v1, used by self attention).  Returns through smem: s_out[64] = unnormalised sum_j p_j v_j,
 // *s_m = running max (log2 domain), *s_l = sum_j p_j.
 template <int NT>
-__device__ __forceinline__ void attend_one_query(const float* q_global /*[64] f32, global or shared*/, const __nv_bfloat16* __restrict__ K,
+__device__ __forceinline__ void attend_one_query(const float* __restrict__ q_global /*[64] f32*/, const __nv_bfloat16* __restrict__ K,
                                                  const __nv_bfloat16* __restrict__ V, int k_begin, int k_end, const float* k1,
                                                  const float* v1, float* s_scores, float* s_red, float* s_out, float* s_ml) {
   constexpr int NW = NT / 32;
@@ -285,10 +285,8 @@ constexpr int kCrossThreads = 256;
 __global__ void __launch_bounds__(kCrossThreads) cross_attention_decode_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                                                                               const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ out,
                                                                               int n_head, int T, int n_split, float* __restrict__ part_m,
-                                                                              float* __restrict__ part_l, float* __restrict__ part_o, int n_q_parts,
-                                                                              long q_part_stride, const float* __restrict__ q_bias) {
+                                                                              float* __restrict__ part_l, float* __restrict__ part_o) {
   __shared__ float s_scores[kCrossThreads / 32 * 64 > 1504 ? kCrossThreads / 32 * 64 : 1504];
-  __shared__ float s_q[64];
   __shared__ float s_red[kCrossThreads / 32];
   __shared__ float s_out[64];
   __shared__ float s_ml[2];
@@ -299,15 +297,8 @@ __global__ void __launch_bounds__(kCrossThreads) cross_attention_decode_kernel(c
   const long kv_off = ((long)b * n_head + h) * T * 64;
   const int per = (T + n_split - 1) / n_split;
   const int k_begin = sp * per, k_end = min(T, k_begin + per);
-  // the query may arrive as split-K partials of the q projection: sum them (fixed order) + bias into smem
-  if (threadIdx.x < 64) {
-    const long qi = (long)b * d + h * 64 + threadIdx.x;
-    float a = q_bias != nullptr ? q_bias[h * 64 + threadIdx.x] : 0.f;
-    for (int pi = 0; pi < n_q_parts; ++pi) a += q[pi * q_part_stride + qi];
-    s_q[threadIdx.x] = a;
-  }
-  __syncthreads();
-  attend_one_query<kCrossThreads>(s_q, k + kv_off, v + kv_off, k_begin, k_end, nullptr, nullptr, s_scores, s_red, s_out, s_ml);
+  attend_one_query<kCrossThreads>(q + (long)b * d + h * 64, k + kv_off, v + kv_off, k_begin, k_end, nullptr, nullptr, s_scores, s_red,
+                                  s_out, s_ml);
   pdl_launch_dependents();  // multi-wave kernel: let the successor start only in this CTA's tail
   if (n_split == 1) {
     if (threadIdx.x < 64) out[(long)b * d + h * 64 + threadIdx.x] = __float2bfloat16_rn(s_out[threadIdx.x] / s_ml[1]);
@@ -407,11 +398,9 @@ int cross_attention_pick_split(int B, int n_head) {
 }
 
 void launch_cross_attention_decode(const float* q, const __nv_bfloat16* k, const __nv_bfloat16* v, __nv_bfloat16* out, int B, int n_head,
-                                   int T, int n_split, float* part_m, float* part_l, float* part_o, cudaStream_t stream, bool pdl,
-                                   int n_q_parts, long q_part_stride, const float* q_bias) {
+                                   int T, int n_split, float* part_m, float* part_l, float* part_o, cudaStream_t stream, bool pdl) {
   dim3 grid(n_head * n_split, B);
-  launch_k(pdl, cross_attention_decode_kernel, grid, dim3(kCrossThreads), 0, stream, q, k, v, out, n_head, T, n_split, part_m, part_l, part_o,
-           n_q_parts, q_part_stride, q_bias);
+  launch_k(pdl, cross_attention_decode_kernel, grid, dim3(kCrossThreads), 0, stream, q, k, v, out, n_head, T, n_split, part_m, part_l, part_o);
   if (n_split > 1) launch_pdl(cross_attention_combine_kernel, dim3(n_head, B), dim3(64), 0, stream, part_m, part_l, part_o, out, n_head, n_split);
 }
 

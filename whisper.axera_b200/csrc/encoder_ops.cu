@@ -17,35 +17,21 @@ namespace {
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kLnMaxVec = 10;
 
-// kAccum: the residual stream is first completed with the pending split-K partials of the previous GEMM,
-// x += bias + parts[0] + parts[1] + ... (fixed order -> deterministic), written back, then normalised.
-template <bool kAccum>
-__global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, const float* __restrict__ gamma,
-                                                        const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, int rows, int d,
-                                                        const float* __restrict__ parts, int n_parts, long part_stride,
-                                                        const float* __restrict__ bias) {
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, int rows, int d) {
   pdl_wait();
   pdl_launch_dependents();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const int nvec = d >> 7;  // float4 per lane (d is a multiple of 128)
-  float4* xr = reinterpret_cast<float4*>(x + (long)warp * d);
+  const float4* xr = reinterpret_cast<const float4*>(x + (long)warp * d);
   float4 v[kLnMaxVec];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < kLnMaxVec; ++i) {
     if (i < nvec) {
       v[i] = xr[i * 32 + lane];
-      if constexpr (kAccum) {
-        const float4 bv = reinterpret_cast<const float4*>(bias)[i * 32 + lane];
-        v[i].x += bv.x, v[i].y += bv.y, v[i].z += bv.z, v[i].w += bv.w;
-        for (int pi = 0; pi < n_parts; ++pi) {
-          const float4 pv = reinterpret_cast<const float4*>(parts + pi * part_stride + (long)warp * d)[i * 32 + lane];
-          v[i].x += pv.x, v[i].y += pv.y, v[i].z += pv.z, v[i].w += pv.w;
-        }
-        xr[i * 32 + lane] = v[i];
-      }
       s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
   }
@@ -294,21 +280,12 @@ void launch_layernorm(const float* x, const float* gamma, const float* beta, __n
   // a decoder step normalises only B rows: spread them over more CTAs and let the launch overlap its predecessor (PDL)
   const int warps_per_cta = rows <= 1024 ? 2 : 8;
   const dim3 grid((rows + warps_per_cta - 1) / warps_per_cta), block(warps_per_cta * 32);
-  float* xm = const_cast<float*>(x);  // not written when kAccum == false
   if (rows <= 1024) {
-    launch_pdl(layernorm_kernel<false>, grid, block, 0, stream, xm, gamma, beta, y, rows, d, (const float*)nullptr, 0, 0L, (const float*)nullptr);
+    launch_pdl(layernorm_kernel, grid, block, 0, stream, x, gamma, beta, y, rows, d);
   } else {
-    layernorm_kernel<false><<<grid, block, 0, stream>>>(xm, gamma, beta, y, rows, d, nullptr, 0, 0L, nullptr);
+    layernorm_kernel<<<grid, block, 0, stream>>>(x, gamma, beta, y, rows, d);
     CUDA_CHECK(cudaGetLastError());
   }
-}
-
-void launch_layernorm_accum(float* x, const float* parts, int n_parts, long part_stride, const float* bias, const float* gamma, const float* beta,
-                            __nv_bfloat16* y, int rows, int d, cudaStream_t stream) {
-  if (d % 128 != 0 || d > 128 * kLnMaxVec) throw CudaError("layernorm: d must be a multiple of 128 and <= 1280");
-  const int warps_per_cta = 2;
-  const dim3 grid((rows + warps_per_cta - 1) / warps_per_cta), block(warps_per_cta * 32);
-  launch_pdl(layernorm_kernel<true>, grid, block, 0, stream, x, gamma, beta, y, rows, d, parts, n_parts, part_stride, bias);
 }
 
 void encoder_ops_set_attributes() {

@@ -168,7 +168,6 @@ Engine::Engine(const std::string& model_root, const std::string& model_type, int
   CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
   CUDA_CHECK(cudaStreamCreateWithFlags(&stream2_, cudaStreamNonBlocking));
   micro_batch_ = getenv("B200W_NO_MICROBATCH") == nullptr;
-  if (const char* mm = getenv("B200W_MICROBATCH_MIN")) micro_batch_min_ = atoi(mm);
   CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&pinned_flags_), 4096 * sizeof(int)));
 
   const std::string dir = model_root + "/" + model_type;  // {root}/{type}/{type}-*  (Whisper.cpp:87-90)
@@ -368,8 +367,7 @@ void Engine::ensure_capacity(int B, long max_samples) {
   dec_rows_pad_ = (cap_ + 127) / 128 * 128;
   x_dec_ = dev_alloc<float>(o, (size_t)dec_rows_pad_ * d);
   qkv_dec_ = dev_alloc<float>(o, (size_t)dec_rows_pad_ * 3 * d);
-  q_dec_ = dev_alloc<float>(o, (size_t)kMaxSplits * dec_rows_pad_ * d);   // split-K partials of the cross-attention q projection
-  part_x_ = dev_alloc<float>(o, (size_t)kMaxSplits * dec_rows_pad_ * d);  // split-K partials of the residual GEMMs (out / cross-out / fc2)
+  q_dec_ = dev_alloc<float>(o, (size_t)dec_rows_pad_ * d);
   h_dec_ = dev_alloc<__nv_bfloat16>(o, (size_t)dec_rows_pad_ * d);
   attn_dec_ = dev_alloc<__nv_bfloat16>(o, (size_t)dec_rows_pad_ * d);
   mlp_dec_ = dev_alloc<__nv_bfloat16>(o, (size_t)dec_rows_pad_ * 4 * d);
@@ -440,16 +438,15 @@ void Engine::build_plans() {
     p_crosskv_ = keep(gemm_plan_create(a, w_crosskv_, 2 * cfg_.l_dec * d, 256, EPI_CROSSKV_BF16, two, tma_out ? &o_kv : nullptr));
   }
   dec_plans_.resize(cfg_.l_dec);
-  const char* bn_env = getenv("B200W_DEC_BN");
-  const int bn = bn_env ? atoi(bn_env) : 32;  // N tile of the decoder-step GEMMs (32 / 64 / 128): narrow = more CTAs streaming W
+  const int bn = 64;
   for (int i = 0; i < cfg_.l_dec; ++i) {
     const LayerDec& L = dec_[i];
     dec_plans_[i].qkv = keep(gemm_plan_create(flat(h_dec_, d, dec_rows_pad_), L.w_qkv, 3 * d, bn, EPI_BIAS_F32));
-    dec_plans_[i].out = keep(gemm_plan_create(flat(attn_dec_, d, dec_rows_pad_), L.w_out, d, bn, EPI_BIAS_F32));
+    dec_plans_[i].out = keep(gemm_plan_create(flat(attn_dec_, d, dec_rows_pad_), L.w_out, d, bn, EPI_BIAS_RESID_F32));
     dec_plans_[i].cq = keep(gemm_plan_create(flat(h_dec_, d, dec_rows_pad_), L.w_cq, d, bn, EPI_BIAS_F32));
-    dec_plans_[i].co = keep(gemm_plan_create(flat(attn_dec_, d, dec_rows_pad_), L.w_co, d, bn, EPI_BIAS_F32));
+    dec_plans_[i].co = keep(gemm_plan_create(flat(attn_dec_, d, dec_rows_pad_), L.w_co, d, bn, EPI_BIAS_RESID_F32));
     dec_plans_[i].fc1 = keep(gemm_plan_create(flat(h_dec_, d, dec_rows_pad_), L.w_fc1, 4 * d, bn, EPI_BIAS_GELU_BF16));
-    dec_plans_[i].fc2 = keep(gemm_plan_create(flat(mlp_dec_, 4 * d, dec_rows_pad_), L.w_fc2, d, bn, EPI_BIAS_F32));
+    dec_plans_[i].fc2 = keep(gemm_plan_create(flat(mlp_dec_, 4 * d, dec_rows_pad_), L.w_fc2, d, bn, EPI_BIAS_RESID_F32));
   }
   p_logits_ = keep(gemm_plan_create(flat(h_dec_, d, dec_rows_pad_), w_emb_bf16_, vocab_pad_, 128, EPI_ARGMAX));
 }
@@ -520,7 +517,7 @@ void Engine::run_encoder(int B) {
 // two cross-attention kernels alternate instead of competing; sequences are independent, so results do not change.
 void Engine::enqueue_decode_step(int B, bool want_logits, bool finalize, int honor_eot) {
   const int d = cfg_.d, H = cfg_.n_head, Ld = cfg_.l_dec;
-  const int n_mb = (micro_batch_ && B >= micro_batch_min_) ? 2 : 1;
+  const int n_mb = (micro_batch_ && B >= 32) ? 2 : 1;
   struct MB {
     int b0, nb;
     cudaStream_t s;
@@ -532,26 +529,12 @@ void Engine::enqueue_decode_step(int B, bool want_logits, bool finalize, int hon
     CUDA_CHECK(cudaEventRecord(ev_fork, stream_));
     CUDA_CHECK(cudaStreamWaitEvent(stream2_, ev_fork, 0));
   }
-  const long part_stride = (long)dec_rows_pad_ * d;
-  auto gp = [&](const MB& m, void* out, size_t elem, long ldo, int N, const float* bias, int splits = 1) {
+  auto gp = [&](const MB& m, void* out, size_t elem, long ldo, int N, const float* bias) {
     GemmParams q{};
     q.rows_valid = m.nb, q.N = N, q.out = static_cast<char*>(out) + (size_t)m.b0 * ldo * elem, q.ldo = ldo, q.bias = bias, q.n_batch = 1;
     q.use_pdl = 1, q.a_row_offset = m.b0;
-    q.k_splits = splits, q.split_stride = part_stride;
     return q;
   };
-  // The three residual GEMMs of a block (self-attention out, cross-attention out, fc2) and the cross-attention q projection
-  // are split along K over several CTAs each (4-8 k-blocks per CTA: one DRAM round trip instead of a serial 12-48 block
-  // loop on 24 CTAs).  Their fp32 partial tiles are summed in a fixed order by the consumer: the next LayerNorm folds
-  // them (+ bias) into the residual stream, the cross-attention kernel sums the q partials while loading the query.
-  const int kb_d = d / 64;
-  auto pick_splits = [](int kb, int per) {  // ~`per` k-blocks per CTA, at most kMaxSplits CTAs, no empty split
-    int s = std::min(kMaxSplits, (kb + per - 1) / per);
-    const int kbps = (kb + s - 1) / s;
-    return (kb + kbps - 1) / kbps;
-  };
-  const int s_d = pick_splits(kb_d, 4);      // K = d
-  const int s_f = pick_splits(4 * kb_d, 8);  // K = 4d
   for (int i = 0; i < n_mb; ++i) {
     DecodeState st = st_;
     st.tokens += (size_t)mb[i].b0 * kTextCtx;
@@ -566,17 +549,13 @@ void Engine::enqueue_decode_step(int B, bool want_logits, bool finalize, int hon
       const size_t skv_off = ((size_t)l * cap_ + m.b0) * H * kTextCtx * 64;
       float* x = x_dec_ + (size_t)m.b0 * d;
       __nv_bfloat16* h = h_dec_ + (size_t)m.b0 * d;
-      const float* px = part_x_ + (size_t)m.b0 * d;
-      if (l == 0)
-        launch_layernorm(x, L.ln1_g, L.ln1_b, h, m.nb, d, m.s);
-      else  // fold in the previous block's fc2 partials
-        launch_layernorm_accum(x, px, s_f, part_stride, dec_[l - 1].b_fc2, L.ln1_g, L.ln1_b, h, m.nb, d, m.s);
+      launch_layernorm(x, L.ln1_g, L.ln1_b, h, m.nb, d, m.s);
       gemm_launch(P.qkv, gp(m, qkv_dec_, 4, 3 * d, 3 * d, L.b_qkv), m.s);
       launch_self_attention_decode(qkv_dec_ + (size_t)m.b0 * 3 * d, self_k_ + skv_off, self_v_ + skv_off, st_.step,
                                    attn_dec_ + (size_t)m.b0 * d, m.nb, H, kTextCtx, m.s);
-      gemm_launch(P.out, gp(m, part_x_, 4, d, d, nullptr, s_d), m.s);
-      launch_layernorm_accum(x, px, s_d, part_stride, L.b_out, L.lnx_g, L.lnx_b, h, m.nb, d, m.s);
-      gemm_launch(P.cq, gp(m, q_dec_, 4, d, d, nullptr, s_d), m.s);
+      gemm_launch(P.out, gp(m, x_dec_, 4, d, d, L.b_out), m.s);
+      launch_layernorm(x, L.lnx_g, L.lnx_b, h, m.nb, d, m.s);
+      gemm_launch(P.cq, gp(m, q_dec_, 4, d, d, L.b_cq), m.s);
     }
     for (int i = 0; i < n_mb; ++i) {
       const MB& m = mb[i];
@@ -589,8 +568,7 @@ void Engine::enqueue_decode_step(int B, bool want_logits, bool finalize, int hon
         if (i == 1) CUDA_CHECK(cudaStreamWaitEvent(m.s, step_events_[2 + 2 * l], 0));
       }
       launch_cross_attention_decode(q_dec_ + (size_t)m.b0 * d, cross_k_ + ckv_off, cross_v_ + ckv_off, attn_dec_ + (size_t)m.b0 * d, m.nb, H,
-                                    kAudioCtx, n_split, part_m_ + po, part_l_ + po, part_o_ + po * 64, m.s, /*pdl=*/n_mb == 1, s_d, part_stride,
-                                    L.b_cq);
+                                    kAudioCtx, n_split, part_m_ + po, part_l_ + po, part_o_ + po * 64, m.s, /*pdl=*/n_mb == 1);
       if (n_mb == 2) CUDA_CHECK(cudaEventRecord(step_events_[2 + 2 * l + i], m.s));
       launches_ += 1 + (n_split > 1 ? 1 : 0);
     }
@@ -598,18 +576,16 @@ void Engine::enqueue_decode_step(int B, bool want_logits, bool finalize, int hon
       const MB& m = mb[i];
       float* x = x_dec_ + (size_t)m.b0 * d;
       __nv_bfloat16* h = h_dec_ + (size_t)m.b0 * d;
-      const float* px = part_x_ + (size_t)m.b0 * d;
-      gemm_launch(P.co, gp(m, part_x_, 4, d, d, nullptr, s_d), m.s);
-      launch_layernorm_accum(x, px, s_d, part_stride, L.b_co, L.ln2_g, L.ln2_b, h, m.nb, d, m.s);
+      gemm_launch(P.co, gp(m, x_dec_, 4, d, d, L.b_co), m.s);
+      launch_layernorm(x, L.ln2_g, L.ln2_b, h, m.nb, d, m.s);
       gemm_launch(P.fc1, gp(m, mlp_dec_, 2, 4 * d, 4 * d, L.b_fc1), m.s);
-      gemm_launch(P.fc2, gp(m, part_x_, 4, d, d, nullptr, s_f), m.s);
+      gemm_launch(P.fc2, gp(m, x_dec_, 4, d, d, L.b_fc2), m.s);
     }
     launches_ += 10 * n_mb;
   }
   for (int i = 0; i < n_mb; ++i) {
     const MB& m = mb[i];
-    launch_layernorm_accum(x_dec_ + (size_t)m.b0 * d, part_x_ + (size_t)m.b0 * d, s_f, part_stride, dec_[Ld - 1].b_fc2, dec_ln_g_, dec_ln_b_,
-                           h_dec_ + (size_t)m.b0 * d, m.nb, d, m.s);
+    launch_layernorm(x_dec_ + (size_t)m.b0 * d, dec_ln_g_, dec_ln_b_, h_dec_ + (size_t)m.b0 * d, m.nb, d, m.s);
     GemmParams p = gp(m, want_logits ? logits_ : nullptr, 4, vocab_pad_, cfg_.n_vocab, nullptr);
     if (!want_logits) p.out = nullptr;
     p.part_val = part_val_ + (size_t)m.b0 * logits_tiles_, p.part_idx = part_idx_ + (size_t)m.b0 * logits_tiles_, p.part_ld = logits_tiles_;

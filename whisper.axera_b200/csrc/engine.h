@@ -19,7 +19,6 @@ constexpr int kAudioCtx = 1500;   // n_audio_ctx
 constexpr int kTextCtx = 448;     // n_text_ctx
 constexpr int kMelFrames = 3000;
 constexpr int kChunkSamples = 480000;
-constexpr int kMaxSplits = 8;      // split-K factor cap of the decoder-step GEMMs
 constexpr int kSotLen = 4;        // {sot, language, transcribe, no_timestamps}, Whisper.cpp:139
 
 struct ModelConfig {              // the keys Whisper::load_models reads (Whisper.cpp:93-137) + the dims our kernels need
@@ -124,7 +123,6 @@ class Engine {
   cudaStream_t stream2_ = nullptr;          // second micro-batch of a decoder step
   std::vector<cudaEvent_t> step_events_;    // fork / join / per-layer cross-attention hand-over
   bool micro_batch_ = true;
-  int micro_batch_min_ = 32;                // smallest batch that is split into two micro-batches
   int cap_ = 0;
   int enc_sub_ = 0;
   bool attn_mma_sync_ = false;
@@ -148,7 +146,7 @@ class Engine {
   float* x_enc_ = nullptr;
   __nv_bfloat16 *h_enc_ = nullptr, *qkv_enc_ = nullptr, *attn_enc_ = nullptr, *mlp_enc_ = nullptr;
   __nv_bfloat16 *cross_k_ = nullptr, *cross_v_ = nullptr, *self_k_ = nullptr, *self_v_ = nullptr;
-  float *x_dec_ = nullptr, *qkv_dec_ = nullptr, *q_dec_ = nullptr, *logits_ = nullptr, *part_x_ = nullptr;
+  float *x_dec_ = nullptr, *qkv_dec_ = nullptr, *q_dec_ = nullptr, *logits_ = nullptr;
   __nv_bfloat16 *h_dec_ = nullptr, *attn_dec_ = nullptr, *mlp_dec_ = nullptr;
   float *part_val_ = nullptr, *part_m_ = nullptr, *part_l_ = nullptr, *part_o_ = nullptr;
   int* part_idx_ = nullptr;

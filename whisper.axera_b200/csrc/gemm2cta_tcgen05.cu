@@ -238,7 +238,6 @@ gemm2cta_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
 
   auto tile_of = [&](int t) {
     TileCoord c;
-    c.split = 0;
     c.n_blk = t % g.n_tiles;
     const int mp = t / g.n_tiles;
     c.m_blk = (mp % g.m_tiles_per_batch) * 2 + (int)rank;  // m_tiles_per_batch counts PAIRS of 128-row tiles here
@@ -366,7 +365,6 @@ void gemm2cta_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
   GemmGeom g{};
   g.n_batch = p.n_batch > 0 ? p.n_batch : n_batch;
   g.n_taps = n_taps, g.kb_per_tap = kb_per_tap, g.num_k_blocks = n_taps * kb_per_tap;
-  g.k_splits = 1, g.kb_per_split = kb_per_tap;
   for (int t = 0; t < 3; ++t) g.a_c0[t] = a_c0[t], g.a_row[t] = a_row[t], g.w_k0[t] = w_k0[t];
   const int m_tiles = (p.rows_valid + BLOCK_M - 1) / BLOCK_M;
   g.m_tiles_per_batch = (m_tiles + 1) / 2;  // pairs

@@ -15,7 +15,6 @@ constexpr int UMMA_K = 16;
 
 struct TileCoord {
   int batch, m_blk, n_blk;
-  int split;  // split-K index (0 for an unsplit GEMM)
 };
 
 struct GemmGeom {
@@ -24,9 +23,6 @@ struct GemmGeom {
   // a_c0[t] + k, rows row + a_row[t]) against W columns w_k0[t] + k.  A plain GEMM has one tap.
   int n_taps, kb_per_tap;
   int a_c0[3], a_row[3], w_k0[3];
-  // split-K (decoder-step GEMMs): every output tile is computed by k_splits CTAs over kb_per_split k-blocks each; the
-  // partial tiles are stored separately (p.split_stride apart) and summed in a fixed order by the consumer kernel.
-  int k_splits, kb_per_split;
 };
 
 // Epilogue of one accumulator tile, executed by all kEpiWarps epilogue warps of a CTA (epi_warp = 0..kEpiWarps-1, its
@@ -43,7 +39,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const TileCoo
   const int row_in_tile = lg * 32 + lane;
   const int r = c.m_blk * BLOCK_M + row_in_tile;  // row within the batch
   const bool row_ok = r < p.rows_valid;
-  const long orow = (long)c.batch * p.out_batch_pitch + (long)(r + p.out_row_offset) * p.ldo + (long)c.split * p.split_stride;
+  const long orow = (long)c.batch * p.out_batch_pitch + (long)(r + p.out_row_offset) * p.ldo;
   const int ch0 = half * CH_PER_WARP;
   // while the MMAs of this tile run: stage the tile's bias slice in smem, prefetch the first chunk's residual / pos rows
   for (int i = etid; i < BLOCK_N; i += kEpiThreads) {

@@ -50,8 +50,6 @@ struct GemmCfg {
 
 __device__ __forceinline__ TileCoord tile_coord(int t, const GemmGeom& g) {
   TileCoord c;
-  c.split = t % g.k_splits;  // the CTAs of one output tile are adjacent in the schedule
-  t /= g.k_splits;
   c.n_blk = t % g.n_tiles;
   int mt = t / g.n_tiles;
   c.m_blk = mt % g.m_tiles_per_batch;
@@ -109,10 +107,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < g.total_tiles; t += gridDim.x) {
         const TileCoord c = tile_coord(t, g);
-        const int kb_lo = g.k_splits > 1 ? c.split * g.kb_per_split : 0;
-        const int kb_hi = g.k_splits > 1 ? min(g.kb_per_tap, kb_lo + g.kb_per_split) : g.kb_per_tap;
         for (int tap = 0; tap < g.n_taps; ++tap) {
-          for (int kb = kb_lo; kb < kb_hi; ++kb) {
+          for (int kb = 0; kb < g.kb_per_tap; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             unsigned char* sa = smem + stage * Cfg::kStageBytes;
             unsigned char* sb = sa + Cfg::kStageBytesA;
@@ -139,12 +135,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         mbar_wait(&tmem_empty_bar[acc_stage], acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + acc_stage * BLOCK_N;
-        int n_kb = g.num_k_blocks;
-        if (g.k_splits > 1) {
-          const int split = t % g.k_splits;
-          n_kb = min(g.kb_per_tap, (split + 1) * g.kb_per_split) - split * g.kb_per_split;
-        }
-        for (int kb = 0; kb < n_kb; ++kb) {
+        for (int kb = 0; kb < g.num_k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
@@ -372,12 +363,7 @@ void gemm_launch(const GemmPlan* plan, const GemmParams& p, cudaStream_t stream)
   g.m_tiles_per_batch = (p.rows_valid + BLOCK_M - 1) / BLOCK_M;
   g.n_tiles = (p.N + plan->block_n - 1) / plan->block_n;
   if (p.n_batch > 0) g.n_batch = p.n_batch;
-  g.k_splits = p.k_splits > 1 ? p.k_splits : 1;
-  g.kb_per_split = (g.kb_per_tap + g.k_splits - 1) / g.k_splits;
-  if (g.k_splits > 1 && (g.n_taps != 1 || plan->epilogue != EPI_BIAS_F32 || p.bias != nullptr))
-    throw CudaError("gemm: split-K needs a plain GEMM with the f32 epilogue and no bias");
-  if ((g.k_splits - 1) * g.kb_per_split >= g.kb_per_tap) throw CudaError("gemm: split-K factor leaves an empty split");
-  g.total_tiles = g.n_batch * g.m_tiles_per_batch * g.n_tiles * g.k_splits;
+  g.total_tiles = g.n_batch * g.m_tiles_per_batch * g.n_tiles;
   if (g.total_tiles <= 0) return;
   const int grid = g.total_tiles < kNumSMs ? g.total_tiles : kNumSMs;
   switch (plan->epilogue) {

@@ -72,8 +72,6 @@ struct GemmParams {
   int a_row_offset;      // added to the row coordinate of A (a launch over rows [a_row_offset, a_row_offset + rows_valid))
   int n_batch;           // batches in this launch (<= the plan's n_batch)
   int use_pdl;           // launch with programmatic dependent launch (decoder-step GEMMs)
-  int k_splits;          // > 1: split-K; partial tile s is stored at out + s * split_stride (no bias; EPI_BIAS_F32 only)
-  long split_stride;     // elements between partial outputs
   const float* bias;     // [N] or null
   const float* pos;      // EPI_GELU_POS_F32: [rows_valid][N] f32
   // EPI_CROSSKV_BF16: n = (layer*2 + kv)*d + h*64 + dh ; row = (batch b, t)
@@ -110,10 +108,6 @@ CUtensorMap make_tmap_bf16_sw128(const void* base, int rank, const uint64_t* dim
 // ---- encoder ops (encoder_ops.cu) -----------------------------------------------------------------
 // LayerNorm (eps 1e-5, fp32 statistics): x f32 [rows][d] -> y bf16 [rows][d]
 void launch_layernorm(const float* x, const float* gamma, const float* beta, __nv_bfloat16* y, int rows, int d, cudaStream_t stream);
-// Same, but first folds the pending split-K partials of the previous residual GEMM into the residual stream (fixed order):
-// x += bias + sum_s parts[s]; x is written back, then normalised.  (decoder step)
-void launch_layernorm_accum(float* x, const float* parts, int n_parts, long part_stride, const float* bias, const float* gamma,
-                            const float* beta, __nv_bfloat16* y, int rows, int d, cudaStream_t stream);
 // non-causal multi-head attention over T keys, head_dim 64: qkv bf16 [B*T][3d] -> out bf16 [B*T][d]
 void launch_encoder_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int n_head, cudaStream_t stream);  // mma.sync comparator
 // same contract on tcgen05 tensor cores (attention_tcgen05.cu); this is the product path
@@ -139,11 +133,9 @@ void launch_self_attention_decode(const float* qkv, __nv_bfloat16* k_cache, __nv
                                   __nv_bfloat16* out, int B, int n_head, int n_ctx, cudaStream_t stream);
 // cross attention: q f32 [B][d] over bf16 head-major K/V [B][H][T][64]; out bf16 [B][d].
 // part_* are workspaces for the split-T variant ([B*H*n_split] each, o is [..][64]).
-// q may be given as n_q_parts split-K partials (q_part_stride apart) plus a bias; they are summed while loading.
 void launch_cross_attention_decode(const float* q, const __nv_bfloat16* k, const __nv_bfloat16* v, __nv_bfloat16* out, int B,
                                    int n_head, int T, int n_split, float* part_m, float* part_l, float* part_o,
-                                   cudaStream_t stream, bool pdl = true, int n_q_parts = 1, long q_part_stride = 0,
-                                   const float* q_bias = nullptr);
+                                   cudaStream_t stream, bool pdl = true);
 // reduces the argmax partials, applies teacher forcing / EOT bookkeeping, stores the next token
 void launch_advance_step(int* step, cudaStream_t stream, bool pdl = true);  // *step += 1 (once per decoder step)
 void launch_argmax_finalize(const DecodeState& st, const float* part_val, const int* part_idx, int n_tiles, int part_ld, int B,
