@@ -438,7 +438,8 @@ void Engine::build_plans() {
     p_crosskv_ = keep(gemm_plan_create(a, w_crosskv_, 2 * cfg_.l_dec * d, 256, EPI_CROSSKV_BF16, two, tma_out ? &o_kv : nullptr));
   }
   dec_plans_.resize(cfg_.l_dec);
-  const int bn = 64;
+  const char* bn_env = getenv("B200W_DEC_BN");
+  const int bn = bn_env ? atoi(bn_env) : 32;  // N tile of the decoder-step GEMMs: narrow tiles = more CTAs streaming W (measured best)
   for (int i = 0; i < cfg_.l_dec; ++i) {
     const LayerDec& L = dec_[i];
     dec_plans_[i].qkv = keep(gemm_plan_create(flat(h_dec_, d, dec_rows_pad_), L.w_qkv, 3 * d, bn, EPI_BIAS_F32));
