@@ -58,6 +58,12 @@ AX_WHISPER_API int AX_WHISPER_RunPCMBatch(AX_WHISPER_HANDLE handle, const float*
 AX_WHISPER_API int AX_WHISPER_RunPCMTokens(AX_WHISPER_HANDLE handle, const float* const* pcm_data, const int* num_samples, int batch,
                                            int max_new_tokens, int honor_eot, int* tokens, int max_tokens, int* n_tokens);
 
+/* Long-form extension (BASELINE.json configs[4]): the reference transcribes only the first 30 s (Whisper.cpp:172); this
+ * entry point cuts the audio into consecutive 30 s windows (the last one may be shorter; a tail under 201 samples is
+ * dropped), transcribes them as one data-parallel batch (window_batch windows per pass, <= 0 for all at once) and
+ * concatenates the window texts in order.  Windows are independent: no timestamps, no previous-text conditioning. */
+AX_WHISPER_API int AX_WHISPER_RunPCMLong(AX_WHISPER_HANDLE handle, const float* pcm_data, long num_samples, int window_batch, char** result);
+
 /* Text of the last error on this thread ("" if none). */
 AX_WHISPER_API const char* AX_WHISPER_LastError(void);
 

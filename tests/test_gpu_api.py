@@ -64,6 +64,17 @@ def test_batch_equals_single_and_is_deterministic(whisper):
         assert whisper.run_tokens([a], max_new_tokens=24, honor_eot=False)[0] == batch[i]
 
 
+def test_long_form_windows(whisper):
+    """configs[4] shape: audio longer than 30 s is cut into independent 30 s windows; the result is the concatenation of the
+    per-window transcriptions, whatever the batch size used to process them."""
+    a = np.concatenate([util.synth_audio("S", 480000, 31), util.synth_audio("N", 480000, 32), util.synth_audio("U", 123456, 33)])
+    text = whisper.run_long(a)
+    parts = [whisper.run(a[i:i + 480000]) for i in range(0, len(a), 480000)]
+    assert text == "".join(parts)
+    assert whisper.run_long(a, window_batch=2) == text
+
+
+
 def test_error_conventions(pkg, whisper, tmp_path):
     lib = pkg.load_library()
     res = ctypes.c_void_p(1)

@@ -195,15 +195,18 @@ encoder_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, con
       const float m_new = fmaxf(m_run, mx);
       const float alpha = fast_exp2((m_run - m_new) * kScaleLog2);
       const float msc = m_new * kScaleLog2;
-      float rs = 0.f;
+      // packed fp32x2 math (sm_100 FFMA2 / FADD2): half the issue slots for the exp arguments and the row sum
+      const float2 sc2 = make_float2(kScaleLog2, kScaleLog2), nm2 = make_float2(-msc, -msc);
+      float2 rs2 = make_float2(0.f, 0.f);
       uint32_t pk[16];
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
-        const float a0 = fast_exp2(fmaf(__uint_as_float(s0[i]), kScaleLog2, -msc));  // exp2(-inf) = 0 for masked keys
-        const float a1 = fast_exp2(fmaf(__uint_as_float(s0[i + 1]), kScaleLog2, -msc));
-        rs += a0 + a1;
-        pk[i >> 1] = pack_bf16x2(a0, a1);
+        const float2 arg = __ffma2_rn(make_float2(__uint_as_float(s0[i]), __uint_as_float(s0[i + 1])), sc2, nm2);
+        const float2 e = make_float2(fast_exp2(arg.x), fast_exp2(arg.y));  // exp2(-inf) = 0 for masked keys
+        rs2 = __fadd2_rn(rs2, e);
+        pk[i >> 1] = pack_bf16x2(e.x, e.y);
       }
+      const float rs = rs2.x + rs2.y;
       l_run = fmaf(l_run, alpha, rs);
       // P_j -> smem, K-major SWIZZLE_128B: row r at r*128 bytes, 16-byte chunk q (keys 8q..8q+7) at position q ^ (r & 7)
       mbar_wait(&bar.p_free[sb], ((j >> 1) & 1) ^ 1);
@@ -226,11 +229,18 @@ encoder_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, con
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar.o_free[ob]);
         if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+          const float2 al2 = make_float2(alpha, alpha);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = (o[i] + __uint_as_float(t0[i])) * alpha;
+          for (int i = 0; i < 32; i += 2) {
+            const float2 r = __fmul2_rn(__fadd2_rn(make_float2(o[i], o[i + 1]), make_float2(__uint_as_float(t0[i]), __uint_as_float(t0[i + 1]))), al2);
+            o[i] = r.x, o[i + 1] = r.y;
+          }
         } else {  // the running maximum of every row of this warp is unchanged (the common case after the first tiles)
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] += __uint_as_float(t0[i]);
+          for (int i = 0; i < 32; i += 2) {
+            const float2 r = __fadd2_rn(make_float2(o[i], o[i + 1]), make_float2(__uint_as_float(t0[i]), __uint_as_float(t0[i + 1])));
+            o[i] = r.x, o[i + 1] = r.y;
+          }
         }
       }
       m_run = m_new;

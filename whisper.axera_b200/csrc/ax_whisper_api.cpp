@@ -138,6 +138,35 @@ AX_WHISPER_API int AX_WHISPER_RunPCMBatch(AX_WHISPER_HANDLE handle, const float*
   return 0;
 }
 
+AX_WHISPER_API int AX_WHISPER_RunPCMLong(AX_WHISPER_HANDLE handle, const float* pcm_data, long num_samples, int window_batch, char** result) {
+  if (!handle || !pcm_data || !result) return -1;
+  *result = nullptr;
+  WhisperHandle* h = static_cast<WhisperHandle*>(handle);
+  std::vector<const float*> ptrs;
+  std::vector<int> lens;
+  for (long off = 0; off < num_samples; off += kChunkSamples) {
+    const long n = std::min<long>(kChunkSamples, num_samples - off);
+    if (n < 201) break;
+    ptrs.push_back(pcm_data + off);
+    lens.push_back((int)n);
+  }
+  if (ptrs.empty()) {
+    set_err("audio shorter than 201 samples");
+    return -1;
+  }
+  const int total = (int)ptrs.size();
+  const int step = window_batch > 0 ? window_batch : total;
+  std::string text;
+  for (int i = 0; i < total; i += step) {
+    const int nb = std::min(step, total - i);
+    std::vector<std::vector<int>> toks;
+    if (run_batch(h, ptrs.data() + i, lens.data() + i, nb, DecodeOptions(), &toks) != 0) return -1;
+    for (int b = 0; b < nb; ++b) text += detokenize(*h, toks[b]);
+  }
+  *result = strdup(text.c_str());
+  return *result ? 0 : -1;
+}
+
 AX_WHISPER_API int AX_WHISPER_RunPCMTokens(AX_WHISPER_HANDLE handle, const float* const* pcm_data, const int* num_samples, int batch,
                                            int max_new_tokens, int honor_eot, int* tokens, int max_tokens, int* n_tokens) {
   if (!handle || !pcm_data || !num_samples || !tokens || !n_tokens || batch <= 0 || max_tokens <= 0) return -1;

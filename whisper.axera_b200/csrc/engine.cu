@@ -344,7 +344,7 @@ void Engine::ensure_capacity(int B, long max_samples) {
   pcm_stride_ = std::max(stride, pcm_stride_);
   const int d = cfg_.d, H = cfg_.n_head, L = cfg_.l_dec;
   const char* sub_env = getenv("B200W_ENC_SUB_BATCH");
-  enc_sub_ = std::min(cap_, sub_env ? std::max(1, atoi(sub_env)) : 32);
+  enc_sub_ = std::min(cap_, sub_env ? std::max(1, atoi(sub_env)) : 128);  // measured: larger sub-batches are slightly faster
   const size_t rows_sub = (size_t)enc_sub_ * kAudioCtx;
   auto& o = ws_owned_;
   pcm_ = dev_alloc<float>(o, (size_t)cap_ * pcm_stride_, false);
