@@ -132,7 +132,7 @@ def run_reference_arm(args, rank, world):
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    n_chunks = 1
+    n_chunks = 2
     util.load_oracle(args.arch)
     for w in range(args.warmup):
         cpu_reference_pass(args.arch, n_chunks, 8, 9000 + w)  # short warm-up passes (page in weights, thread pools)
@@ -144,7 +144,7 @@ def run_reference_arm(args, rank, world):
         "impl": "reference", "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, world, per_step_chunks=n_chunks),
+        "config": {**workload_config(args, world), "reference_arm": "each step is a bounded sample of this workload: %d x 30 s chunk(s) on the host CPU" % n_chunks},
         "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port" if kind == "port" else "reference",
                          "sample": "%d x 30 s chunk per step, Whisper-%s, 4 SOT + %d greedy steps; mel = %s, encoder/decoder = fp32 torch "
                                    "restatement of the exported graphs (onnxruntime absent)" % (n_chunks, args.arch, args.new_tokens,
@@ -300,7 +300,7 @@ def main():
 
             cores = os.cpu_count() or 1
             _t.set_num_threads(cores)
-            n_chunks = 2
+            n_chunks = 6  # ~15 s of CPU work on this box's 16 host cores
             sec = cpu_reference_pass(args.arch, n_chunks, args.new_tokens, 7000)
             line["cpu_baseline"] = {
                 "value": CHUNK_S * n_chunks / sec, "unit": "audio-s/s", "cores": cores,
