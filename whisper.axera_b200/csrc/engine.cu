@@ -190,6 +190,7 @@ Engine::~Engine() {
   for (void* p : owned_) cudaFree(p);
   if (pinned_flags_) cudaFreeHost(pinned_flags_);
   for (auto& e : step_events_) cudaEventDestroy(e);
+  for (auto& e : copy_events_) cudaEventDestroy(e);
   if (stream2_) cudaStreamDestroy(stream2_);
   if (stream_) cudaStreamDestroy(stream_);
 }
@@ -455,8 +456,10 @@ void Engine::build_plans() {
 // ---------------------------------------------------------------------------------------------------------
 // stages
 // ---------------------------------------------------------------------------------------------------------
-void Engine::run_logmel(int B, int max_samples) {
-  launch_logmel(pcm_, pcm_stride_, n_samples_, max_samples, B, cfg_.n_mels, mel_, mel_tm_, utt_max_, stream_);
+void Engine::run_logmel(int B, int max_samples) { run_logmel_range(0, B, max_samples); }
+void Engine::run_logmel_range(int b0, int nb, int max_samples) {
+  launch_logmel(pcm_ + (size_t)b0 * pcm_stride_, pcm_stride_, n_samples_ + b0, max_samples, nb, cfg_.n_mels,
+                mel_ + (size_t)b0 * cfg_.n_mels * kMelFrames, mel_tm_ + (size_t)b0 * (kMelFrames + 2) * cfg_.n_mels, utt_max_ + b0, stream_);
   launches_ += 3;
 }
 void Engine::run_mel_convert(int B) {
@@ -465,9 +468,13 @@ void Engine::run_mel_convert(int B) {
 }
 
 void Engine::run_encoder(int B) {
+  for (int b0 = 0; b0 < B; b0 += enc_sub_) run_encoder_range(b0, std::min(enc_sub_, B - b0));
+}
+
+void Engine::run_encoder_range(int b0, int nb) {
   const int d = cfg_.d, H = cfg_.n_head;
-  for (int b0 = 0; b0 < B; b0 += enc_sub_) {
-    const int nb = std::min(enc_sub_, B - b0);
+  if (nb > enc_sub_) throw std::runtime_error("encoder sub-batch exceeds its workspace");
+  {
     const int rows = nb * kAudioCtx;
     GemmParams p{};
     // conv1 + GELU -> padded bf16 [nb][3002][d] (row t+1)
@@ -810,21 +817,49 @@ void Engine::transcribe(const float* const* pcm, const int* n_samples, int B, co
     max_samples = std::max(max_samples, n_samples[b]);
   }
   ensure_capacity(B, max_samples);
-  cudaEvent_t e0, e1;
-  CUDA_CHECK(cudaEventCreate(&e0));
-  CUDA_CHECK(cudaEventCreate(&e1));
-  CUDA_CHECK(cudaEventRecord(e0, stream_));
-  for (int b = 0; b < B; ++b)
-    CUDA_CHECK(cudaMemcpyAsync(pcm_ + (size_t)b * pcm_stride_, pcm[b], (size_t)n_samples[b] * 4, cudaMemcpyHostToDevice, stream_));
+  // Front end pipelined against the host->device copies: the PCM of encoder sub-batch s+1 is copied on the second stream
+  // while sub-batch s runs log-mel + encoder on the main stream.
+  cudaEvent_t ev[5];
+  for (auto& e : ev) CUDA_CHECK(cudaEventCreate(&e));
+  const long l0 = launches_;
+  CUDA_CHECK(cudaEventRecord(ev[0], stream_));
   CUDA_CHECK(cudaMemcpyAsync(n_samples_, n_samples, sizeof(int) * B, cudaMemcpyHostToDevice, stream_));
-  CUDA_CHECK(cudaEventRecord(e1, stream_));
-  transcribe_resident(B, max_samples, lang, opt, tokens, times);
-  if (times) {
-    CUDA_CHECK(cudaEventElapsedTime(&times->h2d_ms, e0, e1));
-    times->total_ms += times->h2d_ms;
+  CUDA_CHECK(cudaStreamWaitEvent(stream2_, ev[0], 0));  // the copy stream starts after everything queued so far
+  const int n_sub = (B + enc_sub_ - 1) / enc_sub_;
+  if ((int)copy_events_.size() < n_sub) {
+    const size_t old = copy_events_.size();
+    copy_events_.resize(n_sub);
+    for (size_t i = old; i < copy_events_.size(); ++i) CUDA_CHECK(cudaEventCreateWithFlags(&copy_events_[i], cudaEventDisableTiming));
   }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
+  for (int s = 0; s < n_sub; ++s) {
+    const int b0 = s * enc_sub_, nb = std::min(enc_sub_, B - b0);
+    for (int b = b0; b < b0 + nb; ++b)
+      CUDA_CHECK(cudaMemcpyAsync(pcm_ + (size_t)b * pcm_stride_, pcm[b], (size_t)n_samples[b] * 4, cudaMemcpyHostToDevice, stream2_));
+    CUDA_CHECK(cudaEventRecord(copy_events_[s], stream2_));
+  }
+  for (int s = 0; s < n_sub; ++s) {
+    const int b0 = s * enc_sub_, nb = std::min(enc_sub_, B - b0);
+    CUDA_CHECK(cudaStreamWaitEvent(stream_, copy_events_[s], 0));
+    if (s == 0) CUDA_CHECK(cudaEventRecord(ev[1], stream_));  // first PCM has landed: exposed part of the copy
+    run_logmel_range(b0, nb, max_samples);
+    run_encoder_range(b0, nb);
+  }
+  CUDA_CHECK(cudaEventRecord(ev[2], stream_));
+  const int steps = run_decode(B, sot_sequence(lang), opt, tokens);
+  CUDA_CHECK(cudaEventRecord(ev[3], stream_));
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+  if (times) {
+    CUDA_CHECK(cudaEventElapsedTime(&times->h2d_ms, ev[0], ev[1]));
+    float front = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&front, ev[1], ev[2]));
+    times->mel_ms = 0.f;           // interleaved with the encoder per sub-batch in this path
+    times->encoder_ms = front;     // log-mel + encoder (+ the copies they overlap)
+    CUDA_CHECK(cudaEventElapsedTime(&times->decode_ms, ev[2], ev[3]));
+    CUDA_CHECK(cudaEventElapsedTime(&times->total_ms, ev[0], ev[3]));
+    times->decode_steps = steps;
+    times->kernel_launches = launches_ - l0;
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
 }
 
 }  // namespace b200w

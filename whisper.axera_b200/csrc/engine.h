@@ -86,6 +86,8 @@ class Engine {
   void run_logmel(int B, int max_samples);         // pcm_ -> mel_ (+ bf16 time-major copy for conv1)
   void run_mel_convert(int B);                     // mel_ (f32, caller supplied) -> bf16 time-major copy
   void run_encoder(int B);                         // -> cross K/V cache
+  void run_logmel_range(int b0, int nb, int max_samples);
+  void run_encoder_range(int b0, int nb);          // one encoder sub-batch (nb <= enc_sub)
   // greedy loop; returns number of decoder steps executed. Tokens land in host vector per sequence.
   int run_decode(int B, const std::vector<int>& sot, const DecodeOptions& opt, std::vector<std::vector<int>>* tokens);
 
@@ -122,6 +124,7 @@ class Engine {
   cudaStream_t stream_ = nullptr;
   cudaStream_t stream2_ = nullptr;          // second micro-batch of a decoder step
   std::vector<cudaEvent_t> step_events_;    // fork / join / per-layer cross-attention hand-over
+  std::vector<cudaEvent_t> copy_events_;    // per encoder sub-batch: its PCM has been copied (pipelined transcribe())
   bool micro_batch_ = true;
   int cap_ = 0;
   int enc_sub_ = 0;
