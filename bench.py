@@ -222,11 +222,13 @@ def main():
         sampler.start()
     t0 = time.perf_counter()
     dev_ms, stage, launches = [], [], 0
+    torch.cuda.nvtx.range_push("timed")  # `ncu --nvtx --nvtx-include "timed/"` profiles exactly the timed steps
     for _ in range(args.steps):
         toks, t = eng.transcribe_resident(B, max_new_tokens=args.new_tokens, honor_eot=False)
         dev_ms.append(t["total_ms"])
         stage.append(t)
         launches += t["kernel_launches"]
+    torch.cuda.nvtx.range_pop()
     barrier()
     wall_s = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
