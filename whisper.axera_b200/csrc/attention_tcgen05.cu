@@ -40,6 +40,19 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// explicit shared-space accesses (32-bit addresses): the softmax loop is issue-bound, generic 64-bit address math costs slots
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+// named barrier over the two warps that share a TMEM lane group (ids 1..4)
+__device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
 // MN-major bf16 operand tile [rows = K index][64 elements of N, 128 bytes] written by TMA with SWIZZLE_128B:
 // 8-row groups 1024 bytes apart (stride byte offset); a single 64-element block in the N direction.
 __device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr) {
@@ -166,6 +179,13 @@ encoder_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, con
     const int row = lg * 32 + lane;
     const uint32_t tlane = tmem_base + (static_cast<uint32_t>(lg * 32) << 16);
     float m_run = -INFINITY, l_run = 0.f;
+    // shared-space addresses of this thread's exchange slots and of its four 16-byte chunks of a P row
+    const uint32_t xch_mine = smem_u32(&xch[0][ch][row]), xch_other = smem_u32(&xch[0][ch ^ 1][row]);
+    constexpr uint32_t kXchParity = 2 * kQ * 4;
+    const uint32_t p_row = smem_u32(sP) + row * 128;
+    uint32_t p_chunk[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) p_chunk[q] = p_row + (((ch * 4 + q) ^ (row & 7)) << 4);
     float o[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) o[i] = 0.f;
@@ -189,9 +209,9 @@ encoder_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, con
 #pragma unroll
       for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(s0[i]));
       // the row maximum needs the other half's keys: exchange through smem (double-buffered by tile parity)
-      xch[sb][ch][row] = mx;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      mx = fmaxf(mx, xch[sb][ch ^ 1][row]);
+      st_shared_f32(xch_mine + sb * kXchParity, mx);
+      pair_barrier(1 + lg);
+      mx = fmaxf(mx, ld_shared_f32(xch_other + sb * kXchParity));
       const float m_new = fmaxf(m_run, mx);
       const float alpha = fast_exp2((m_run - m_new) * kScaleLog2);
       const float msc = m_new * kScaleLog2;
@@ -210,10 +230,8 @@ encoder_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, con
       l_run = fmaf(l_run, alpha, rs);
       // P_j -> smem, K-major SWIZZLE_128B: row r at r*128 bytes, 16-byte chunk q (keys 8q..8q+7) at position q ^ (r & 7)
       mbar_wait(&bar.p_free[sb], ((j >> 1) & 1) ^ 1);
-      unsigned char* prow = sP + sb * kPBytes + row * 128;
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        *reinterpret_cast<uint4*>(prow + (((ch * 4 + q) ^ (row & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+      for (int q = 0; q < 4; ++q) st_shared_v4(p_chunk[q] + sb * kPBytes, pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar.p_ready[sb]);
@@ -253,9 +271,11 @@ encoder_attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, con
       tmem_ld_32x32b_x32(tlane + 128 + ob * 64 + ch * 32, t0);
       tcgen05_wait_ld();
       // the row sum is split over the two threads of the row
-      xch[0][ch][row] = l_run;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const float inv = 1.f / (l_run + xch[0][ch ^ 1][row]);
+      // every exchange of the tile loop has been consumed by both threads of the row (they met at the last pair barrier
+      // after reading), parity slot of the next tile index is free
+      st_shared_f32(xch_mine + (n_tiles & 1) * kXchParity, l_run);
+      pair_barrier(1 + lg);
+      const float inv = 1.f / (l_run + ld_shared_f32(xch_other + (n_tiles & 1) * kXchParity));
       if (q0 + row < T) {
         __nv_bfloat16* dst = out + ((long)b * T + q0 + row) * d + h * 64 + ch * 32;
 #pragma unroll

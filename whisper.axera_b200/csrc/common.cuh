@@ -30,28 +30,40 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 // Programmatic dependent launch: the kernel may start while its predecessor on the stream is still running; it must call
 // pdl_wait() before touching global memory.  Used for the launch-latency-bound kernels of a decoder step.
 bool pdl_enabled();
+// Launch priority of the kernels launched through launch_pdl / launch_k (0 = default, negative = more urgent).  The decode
+// step launches its short dependent kernels at high priority so that the block scheduler places them ahead of the still
+// undispatched CTAs of the other micro-batch's long cross-attention kernel.  Captured into graph kernel nodes.
+int& launch_priority();
+struct ScopedLaunchPriority {
+  int saved;
+  explicit ScopedLaunchPriority(int p) : saved(launch_priority()) { launch_priority() = p; }
+  ~ScopedLaunchPriority() { launch_priority() = saved; }
+};
 #ifdef __CUDACC__
 template <class... KArgs, class... Args>
-inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+inline void launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (pdl && pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (launch_priority() != 0) {
+    attr[n].id = cudaLaunchAttributePriority;
+    attr[n].val.priority = launch_priority();
+    ++n;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = n;
   CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
 }
-// same, with the programmatic attribute only if `pdl` (kernels that follow a cross-stream event wait launch plainly)
+// launch with the programmatic-serialization attribute (kernels that follow a cross-stream event wait use launch_k(false, ...))
 template <class... KArgs, class... Args>
-inline void launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
-  if (pdl) {
-    launch_pdl(kernel, grid, block, smem, stream, static_cast<Args&&>(args)...);
-  } else {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = stream;
-    CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
-  }
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  launch_k(true, kernel, grid, block, smem, stream, static_cast<Args&&>(args)...);
 }
 #endif
 

@@ -378,6 +378,11 @@ bool pdl_enabled() {
   return on;
 }
 
+int& launch_priority() {
+  static thread_local int prio = 0;
+  return prio;
+}
+
 void launch_embed(const DecodeState& st, const float* tok_emb, const float* pos_emb, float* x, int B, int d, int n_text_ctx,
                   cudaStream_t stream, bool pdl) {
   launch_k(pdl, embed_kernel, dim3(B), dim3(128), 0, stream, st.step, st.tokens, tok_emb, pos_emb, x, d, n_text_ctx);
@@ -404,7 +409,18 @@ void launch_cross_attention_decode(const float* q, const __nv_bfloat16* k, const
   if (n_split > 1) launch_pdl(cross_attention_combine_kernel, dim3(n_head, B), dim3(64), 0, stream, part_m, part_l, part_o, out, n_head, n_split);
 }
 
-void decode_ops_set_attributes() {}
+void decode_ops_set_attributes() {
+  // The decode-step kernels of one micro-batch run next to the tcgen05 GEMM CTAs of the other one.  An SM cannot host
+  // kernels with different L1/shared splits at the same time, so every kernel of the step asks for the GEMM's (maximum
+  // shared memory) carve-out; none of them relies on L1 hits.
+  if (getenv("B200W_NO_CARVEOUT")) return;
+  CUDA_CHECK(cudaFuncSetAttribute(embed_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  CUDA_CHECK(cudaFuncSetAttribute(self_attention_decode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  CUDA_CHECK(cudaFuncSetAttribute(cross_attention_decode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  CUDA_CHECK(cudaFuncSetAttribute(cross_attention_combine_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  CUDA_CHECK(cudaFuncSetAttribute(argmax_finalize_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  CUDA_CHECK(cudaFuncSetAttribute(advance_step_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+}
 
 void launch_argmax_finalize(const DecodeState& st, const float* part_val, const int* part_idx, int n_tiles, int part_ld, int B,
                             int n_text_ctx, int eot, int honor_eot, int sot_len, cudaStream_t stream) {

@@ -167,7 +167,15 @@ Engine::Engine(const std::string& model_root, const std::string& model_type, int
   if (prop.major != 10) throw CudaError(std::string("this build contains sm_100a code only; device is ") + prop.name);
   CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
   CUDA_CHECK(cudaStreamCreateWithFlags(&stream2_, cudaStreamNonBlocking));
+  {
+    int least = 0, greatest = 0;
+    CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    prio_high_ = greatest;
+  }
   micro_batch_ = getenv("B200W_NO_MICROBATCH") == nullptr;
+  if (const char* e = getenv("B200W_N_MICROBATCH")) n_micro_batch_ = std::max(1, std::min(4, atoi(e)));
+  cross_chain_ = getenv("B200W_NO_CROSS_CHAIN") == nullptr;
+  for (auto& st : mb_streams_) CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&pinned_flags_), 4096 * sizeof(int)));
 
   const std::string dir = model_root + "/" + model_type;  // {root}/{type}/{type}-*  (Whisper.cpp:87-90)
@@ -178,7 +186,7 @@ Engine::Engine(const std::string& model_root, const std::string& model_type, int
   logmel_upload_tables();
   kernels_set_attributes();
   load_weights(dir, model_type);
-  step_events_.resize(2 + 2 * cfg_.l_dec);
+  step_events_.resize(8 + 4 * cfg_.l_dec);
   for (auto& e : step_events_) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   ensure_capacity(std::max(1, max_batch));
 }
@@ -191,6 +199,8 @@ Engine::~Engine() {
   if (pinned_flags_) cudaFreeHost(pinned_flags_);
   for (auto& e : step_events_) cudaEventDestroy(e);
   for (auto& e : copy_events_) cudaEventDestroy(e);
+  for (auto& st : mb_streams_)
+    if (st) cudaStreamDestroy(st);
   if (stream2_) cudaStreamDestroy(stream2_);
   if (stream_) cudaStreamDestroy(stream_);
 }
@@ -525,17 +535,29 @@ void Engine::run_encoder_range(int b0, int nb) {
 // two cross-attention kernels alternate instead of competing; sequences are independent, so results do not change.
 void Engine::enqueue_decode_step(int B, bool want_logits, bool finalize, int honor_eot) {
   const int d = cfg_.d, H = cfg_.n_head, Ld = cfg_.l_dec;
-  const int n_mb = (micro_batch_ && B >= 32) ? 2 : 1;
+  int n_mb = (micro_batch_ && B >= 32) ? n_micro_batch_ : 1;
+  while (n_mb > 1 && B / n_mb < 16) --n_mb;
   struct MB {
     int b0, nb;
     cudaStream_t s;
-  } mb[2];
-  mb[0] = {0, n_mb == 2 ? (B + 1) / 2 : B, stream_};
-  mb[1] = {mb[0].nb, B - mb[0].nb, stream2_};
-  cudaEvent_t ev_fork = step_events_[0], ev_join = step_events_[1];
-  if (n_mb == 2) {
+  } mb[4];
+  cudaStream_t mb_stream[4] = {stream_, stream2_, mb_streams_[0], mb_streams_[1]};
+  for (int i = 0, b0 = 0; i < n_mb; ++i) {
+    const int nb = (B - b0 + (n_mb - i) - 1) / (n_mb - i);
+    mb[i] = {b0, nb, mb_stream[i]};
+    b0 += nb;
+  }
+  // events: [0] fork, [1..3] joins, [8 + 4 l + i] end of micro-batch i's cross attention of layer l
+  cudaEvent_t ev_fork = step_events_[0];
+  auto cross_event = [&](int l, int i) { return step_events_[8 + 4 * l + i]; };
+  // With several micro-batches the short kernels are launched urgent and the long cross-attention kernels at default priority:
+  // the block scheduler then slots another micro-batch's dependent chain in between the cross-attention CTAs.
+  static const bool use_prio = getenv("B200W_NO_PRIORITY") == nullptr;
+  const int prio_small = (n_mb > 1 && use_prio) ? prio_high_ : 0;
+  ScopedLaunchPriority prio_scope(prio_small);
+  if (n_mb > 1) {
     CUDA_CHECK(cudaEventRecord(ev_fork, stream_));
-    CUDA_CHECK(cudaStreamWaitEvent(stream2_, ev_fork, 0));
+    for (int i = 1; i < n_mb; ++i) CUDA_CHECK(cudaStreamWaitEvent(mb[i].s, ev_fork, 0));
   }
   auto gp = [&](const MB& m, void* out, size_t elem, long ldo, int N, const float* bias) {
     GemmParams q{};
@@ -570,14 +592,19 @@ void Engine::enqueue_decode_step(int B, bool want_logits, bool finalize, int hon
       const int n_split = cross_attention_pick_split(m.nb, H);
       const size_t ckv_off = ((size_t)l * cap_ + m.b0) * H * kAudioCtx * 64;
       const size_t po = (size_t)m.b0 * H * 8;
-      if (n_mb == 2) {
-        // micro-batch 0 waits for micro-batch 1's previous cross attention, micro-batch 1 for micro-batch 0's current one
-        if (i == 0 && l > 0) CUDA_CHECK(cudaStreamWaitEvent(m.s, step_events_[2 + 2 * (l - 1) + 1], 0));
-        if (i == 1) CUDA_CHECK(cudaStreamWaitEvent(m.s, step_events_[2 + 2 * l], 0));
+      const bool chain = n_mb > 1 && cross_chain_;
+      if (chain) {
+        // the cross-attention kernels take turns on HBM: micro-batch i waits for micro-batch i-1's kernel of this layer,
+        // micro-batch 0 for the last micro-batch's kernel of the previous layer
+        if (i == 0 && l > 0) CUDA_CHECK(cudaStreamWaitEvent(m.s, cross_event(l - 1, n_mb - 1), 0));
+        if (i > 0) CUDA_CHECK(cudaStreamWaitEvent(m.s, cross_event(l, i - 1), 0));
       }
-      launch_cross_attention_decode(q_dec_ + (size_t)m.b0 * d, cross_k_ + ckv_off, cross_v_ + ckv_off, attn_dec_ + (size_t)m.b0 * d, m.nb, H,
-                                    kAudioCtx, n_split, part_m_ + po, part_l_ + po, part_o_ + po * 64, m.s, /*pdl=*/n_mb == 1);
-      if (n_mb == 2) CUDA_CHECK(cudaEventRecord(step_events_[2 + 2 * l + i], m.s));
+      {
+        ScopedLaunchPriority low(0);
+        launch_cross_attention_decode(q_dec_ + (size_t)m.b0 * d, cross_k_ + ckv_off, cross_v_ + ckv_off, attn_dec_ + (size_t)m.b0 * d, m.nb,
+                                      H, kAudioCtx, n_split, part_m_ + po, part_l_ + po, part_o_ + po * 64, m.s, /*pdl=*/!chain);
+      }
+      if (chain) CUDA_CHECK(cudaEventRecord(cross_event(l, i), m.s));
       launches_ += 1 + (n_split > 1 ? 1 : 0);
     }
     for (int i = 0; i < n_mb; ++i) {
@@ -607,9 +634,9 @@ void Engine::enqueue_decode_step(int B, bool want_logits, bool finalize, int hon
       launches_ += 1;
     }
   }
-  if (n_mb == 2) {
-    CUDA_CHECK(cudaEventRecord(ev_join, stream2_));
-    CUDA_CHECK(cudaStreamWaitEvent(stream_, ev_join, 0));
+  for (int i = 1; i < n_mb; ++i) {
+    CUDA_CHECK(cudaEventRecord(step_events_[i], mb[i].s));
+    CUDA_CHECK(cudaStreamWaitEvent(stream_, step_events_[i], 0));
   }
   if (finalize) {
     launch_advance_step(st_.step, stream_, /*pdl=*/n_mb == 1);

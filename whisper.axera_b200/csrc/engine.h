@@ -123,9 +123,13 @@ class Engine {
   int device_ = 0;
   cudaStream_t stream_ = nullptr;
   cudaStream_t stream2_ = nullptr;          // second micro-batch of a decoder step
+  int prio_high_ = 0;                       // most urgent launch priority of the device (cudaDeviceGetStreamPriorityRange)
   std::vector<cudaEvent_t> step_events_;    // fork / join / per-layer cross-attention hand-over
   std::vector<cudaEvent_t> copy_events_;    // per encoder sub-batch: its PCM has been copied (pipelined transcribe())
   bool micro_batch_ = true;
+  int n_micro_batch_ = 2;                   // micro-batches of a decoder step (B200W_N_MICROBATCH, 1..4)
+  bool cross_chain_ = true;                 // hand the cross-attention kernels over micro-batch to micro-batch with events
+  cudaStream_t mb_streams_[2] = {nullptr, nullptr};  // streams of micro-batches 2 and 3
   int cap_ = 0;
   int enc_sub_ = 0;
   bool attn_mma_sync_ = false;

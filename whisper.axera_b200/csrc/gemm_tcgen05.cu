@@ -241,12 +241,7 @@ inline CUtensorMap make_tmap(const void* base, int rank, const uint64_t* dims, c
 template <int BLOCK_N, int EPI>
 void launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const GemmGeom& g, const GemmParams& p, int grid, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
-  if (p.use_pdl) {
-    launch_pdl(gemm_tcgen05_kernel<BLOCK_N, EPI>, dim3(grid), dim3(Cfg::kThreads), (size_t)Cfg::kSmemBytes, stream, ta, tb, g, p);
-  } else {
-    gemm_tcgen05_kernel<BLOCK_N, EPI><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, g, p);
-    CUDA_CHECK(cudaGetLastError());
-  }
+  launch_k(p.use_pdl != 0, gemm_tcgen05_kernel<BLOCK_N, EPI>, dim3(grid), dim3(Cfg::kThreads), (size_t)Cfg::kSmemBytes, stream, ta, tb, g, p);
 }
 
 template <int EPI>
@@ -264,6 +259,7 @@ void launch_bn(int block_n, const CUtensorMap& ta, const CUtensorMap& tb, const 
 template <int BLOCK_N, int EPI>
 void set_attr_one() {
   CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BLOCK_N>::kSmemBytes));
+  CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, EPI>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
 }
 template <int EPI>
 void set_attr_epi() {
