@@ -409,18 +409,7 @@ void launch_cross_attention_decode(const float* q, const __nv_bfloat16* k, const
   if (n_split > 1) launch_pdl(cross_attention_combine_kernel, dim3(n_head, B), dim3(64), 0, stream, part_m, part_l, part_o, out, n_head, n_split);
 }
 
-void decode_ops_set_attributes() {
-  // The decode-step kernels of one micro-batch run next to the tcgen05 GEMM CTAs of the other one.  An SM cannot host
-  // kernels with different L1/shared splits at the same time, so every kernel of the step asks for the GEMM's (maximum
-  // shared memory) carve-out; none of them relies on L1 hits.
-  if (getenv("B200W_NO_CARVEOUT")) return;
-  CUDA_CHECK(cudaFuncSetAttribute(embed_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  CUDA_CHECK(cudaFuncSetAttribute(self_attention_decode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  CUDA_CHECK(cudaFuncSetAttribute(cross_attention_decode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  CUDA_CHECK(cudaFuncSetAttribute(cross_attention_combine_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  CUDA_CHECK(cudaFuncSetAttribute(argmax_finalize_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  CUDA_CHECK(cudaFuncSetAttribute(advance_step_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-}
+void decode_ops_set_attributes() {}
 
 void launch_argmax_finalize(const DecodeState& st, const float* part_val, const int* part_idx, int n_tiles, int part_ld, int B,
                             int n_text_ctx, int eot, int honor_eot, int sot_len, cudaStream_t stream) {

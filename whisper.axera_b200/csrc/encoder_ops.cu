@@ -289,8 +289,6 @@ void launch_layernorm(const float* x, const float* gamma, const float* beta, __n
 }
 
 void encoder_ops_set_attributes() {
-  if (!getenv("B200W_NO_CARVEOUT"))  // see decode_ops_set_attributes
-    CUDA_CHECK(cudaFuncSetAttribute(layernorm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   CUDA_CHECK(cudaFuncSetAttribute(encoder_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (kQTile * 64 + 4 * kKvTile * 64) * 2));
 }
 

@@ -33,7 +33,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const TileCoo
                                               uint32_t acc_phase, int epi_warp, int lg, int lane) {
   constexpr int kEpiThreads = kEpiWarps * 32;
   constexpr int CH_PER_WARP = (BLOCK_N / 32) / (kEpiWarps / 4);
-  constexpr bool kHasExtra = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_GELU_POS_F32);
+  // the residual update x += acc + bias is a vector reduction at L2 (red.global.add.v4.f32): no read of x in the epilogue,
+  // no registers holding it; one add per element per kernel, so the result is the same as load-add-store
+  constexpr bool kHasExtra = (EPI == EPI_GELU_POS_F32);
   const int half = epi_warp >> 2;
   const int etid = epi_warp * 32 + lane;
   const int row_in_tile = lg * 32 + lane;
@@ -51,7 +53,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const TileCoo
   auto load_extra = [&](float4(&dst)[8], int ch) {
     if constexpr (kHasExtra) {
       const int n0 = c.n_blk * BLOCK_N + ch * 32;
-      const float* src = (EPI == EPI_BIAS_RESID_F32) ? reinterpret_cast<const float*>(p.out) + orow + n0 : p.pos + (long)r * p.N + n0;
+      const float* src = p.pos + (long)r * p.N + n0;
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         dst[j] = (row_ok && n0 + j * 4 + 4 <= p.N) ? *reinterpret_cast<const float4*>(src + j * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -116,13 +118,17 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const TileCoo
             const float4 rv = extra[i & 1][j >> 2];
             u.x += rv.x, u.y += rv.y, u.z += rv.z, u.w += rv.w;
           }
-          *reinterpret_cast<float4*>(o + j) = u;
+          if constexpr (EPI == EPI_BIAS_RESID_F32) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j), "f"(u.x), "f"(u.y), "f"(u.z), "f"(u.w) : "memory");
+          } else {
+            *reinterpret_cast<float4*>(o + j) = u;
+          }
         }
       } else {
         const float* xs = (EPI == EPI_GELU_POS_F32) ? p.pos + (long)r * p.N + n0 : o;
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (n0 + j < p.N) o[j] = (kHasExtra ? xs[j] : 0.f) + f[j];
+          if (n0 + j < p.N) o[j] = ((kHasExtra || EPI == EPI_BIAS_RESID_F32) ? xs[j] : 0.f) + f[j];
       }
     } else if constexpr (EPI == EPI_CROSSKV_BF16) {
       // n0 is 32-aligned, so the chunk stays inside one (layer, k|v, head) slice of 64 columns

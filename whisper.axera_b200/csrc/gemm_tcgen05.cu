@@ -40,10 +40,12 @@ struct GemmCfg {
   static constexpr int kStageBytesA = BLOCK_M * BLOCK_K * 2;
   static constexpr int kStageBytesB = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-  static constexpr int kStages = kSmemBudget / kStageBytes;  // 256 -> 4, 128 -> 6, 64 -> 8, 32 -> 9
+  static constexpr int kStages = kSmemBudget / kStageBytes > 8 ? 8 : kSmemBudget / kStageBytes;  // 256 -> 4, 128 -> 6, 64 -> 8, 32 -> 8
   static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
   static constexpr int kEpiWarps = BLOCK_N >= 128 ? 8 : 4;  // 8: two warps per TMEM lane group, each taking half of the columns
-  static constexpr int kMinCtas = BLOCK_N >= 128 ? 1 : 2;    // register cap (<= 168) for the narrow tiles
+  // register cap: the BLOCK_N = 32 kernels of a decoder step must fit next to the resident cross-attention CTAs of the
+  // other micro-batch (72 registers x 192 threads = 13.8 K: what one retiring cross-attention CTA frees on an SM plus the 4 K spare)
+  static constexpr int kMaxRegs = BLOCK_N >= 128 ? 168 : (BLOCK_N == 32 ? 72 : 128);
   static constexpr int kThreads = 64 + 32 * kEpiWarps;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * BLOCK_N * 4 /*bias*/;
 };
@@ -58,7 +60,7 @@ __device__ __forceinline__ TileCoord tile_coord(int t, const GemmGeom& g) {
 }
 
 template <int BLOCK_N, int EPI>
-__global__ void __launch_bounds__(GemmCfg<BLOCK_N>::kThreads, GemmCfg<BLOCK_N>::kMinCtas)
+__global__ void __launch_bounds__(GemmCfg<BLOCK_N>::kThreads) __maxnreg__(GemmCfg<BLOCK_N>::kMaxRegs)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmGeom g,
                     const GemmParams p) {
   using Cfg = GemmCfg<BLOCK_N>;
@@ -259,7 +261,6 @@ void launch_bn(int block_n, const CUtensorMap& ta, const CUtensorMap& tb, const 
 template <int BLOCK_N, int EPI>
 void set_attr_one() {
   CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BLOCK_N>::kSmemBytes));
-  CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, EPI>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
 }
 template <int EPI>
 void set_attr_epi() {
