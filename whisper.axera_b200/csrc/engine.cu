@@ -602,8 +602,8 @@ void Engine::enqueue_decode_step(int B, bool want_logits, bool finalize, int hon
       static const bool skip_cross = getenv("B200W_DIAG_SKIP_CROSS") != nullptr;  // timing diagnostic only: results are wrong
       if (!skip_cross) {
         ScopedLaunchPriority low(0);
-        launch_cross_attention_decode(q_dec_ + (size_t)m.b0 * d, cross_k_ + ckv_off, cross_v_ + ckv_off, attn_dec_ + (size_t)m.b0 * d, m.nb,
-                                      H, kAudioCtx, n_split, part_m_ + po, part_l_ + po, part_o_ + po * 64, m.s, /*pdl=*/!chain);
+        launch_cross_attention_decode(q_dec_ + (size_t)m.b0 * d, cross_k_ + ckv_off, cross_v_ + ckv_off, attn_dec_ + (size_t)m.b0 * d,
+                                      m.nb, H, kAudioCtx, n_split, part_m_ + po, part_l_ + po, part_o_ + po * 64, m.s, /*pdl=*/!chain);
       }
       if (chain) CUDA_CHECK(cudaEventRecord(cross_event(l, i), m.s));
       launches_ += 1 + (n_split > 1 ? 1 : 0);
