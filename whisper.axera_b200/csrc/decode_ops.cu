@@ -312,6 +312,137 @@ __global__ void __launch_bounds__(kCrossThreads) cross_attention_decode_kernel(c
   }
 }
 
+// Streaming variant for large batches.  A single resident wave of CTAs (at most three per SM, 64 registers) each works
+// through several (sequence, head) items back to back and keeps its 16-byte loads rolling across the phase and item
+// boundaries: a slot is refilled with the load of the NEXT step (next K block, first V block, first K block of the next
+// item) the moment it has been consumed, so the reductions between the phases never drain the memory pipeline.  Because
+// the whole grid is dispatched at once and leaves ~16 K registers and most of the shared memory of every SM free, the
+// short kernels of the other micro-batch (192-thread tcgen05 GEMM CTAs, LayerNorm, self attention) are placed next to
+// it immediately instead of queueing behind undispatched CTAs.
+constexpr int kXU = 8;                                        // rolling loads per thread
+constexpr int kXKeysPerStep = (kCrossThreads / 32) * 4 * kXU;  // 256 keys per step
+constexpr int kXMaxT = 1536;
+__global__ void __maxnreg__(64)
+cross_attention_stream_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
+                              __nv_bfloat16* __restrict__ out, int n_head, int T, int n_items, int items_per_cta) {
+  constexpr int NW = kCrossThreads / 32;
+  __shared__ float s_scores[kXMaxT];
+  __shared__ float s_acc[NW * 64];
+  __shared__ float s_redm[NW], s_redl[NW];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grp = lane >> 3, sub = lane & 7;  // 4 keys per warp instruction, 8 lanes (16 B each) per key
+  const int first = blockIdx.x * items_per_cta;
+  const int last = min(n_items, first + items_per_cta);
+  const int d = n_head * 64;
+  const int nk = (T + kXKeysPerStep - 1) / kXKeysPerStep;  // steps per phase
+  const int spi = 2 * nk;                                  // steps per item
+  const int total = (last - first) * spi;
+  const int key0 = warp * 4 + grp;                         // key of slot 0 within a step; slot u adds 32 u
+  pdl_wait();
+  if (total <= 0) return;
+
+  // slot u of step (item, st): tensor K for st < nk else V, key (st % nk) * 256 + 32 u + key0
+  auto step_ptr = [&](int item, int st) {
+    const __nv_bfloat16* base = (st < nk ? k : v) + (long)item * T * 64;  // items are (b, h) pairs = the cache's own order
+    const int kb = (st < nk ? st : st - nk) * kXKeysPerStep + key0;
+    return base + (long)kb * 64 + sub * 8;
+  };
+  auto step_key = [&](int st) { return (st < nk ? st : st - nk) * kXKeysPerStep + key0; };
+
+  uint4 kv[kXU];
+  {
+    const __nv_bfloat16* p0 = step_ptr(first, 0);
+    const int j0 = step_key(0);
+#pragma unroll
+    for (int u = 0; u < kXU; ++u) kv[u] = (j0 + 32 * u < T) ? ld_stream16(p0 + u * 32 * 64) : make_uint4(0, 0, 0, 0);
+  }
+  float qr[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) qr[i] = q[(long)first * 64 + sub * 8 + i] * kScoreScaleLog2;  // q is [B][H*64]: item * 64
+
+  float mx = -INFINITY, m = 0.f, lsum = 0.f;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  int item = first, st = 0;
+  for (int g = 0; g < total; ++g) {
+    // the step after this one (its loads are issued slot by slot while this step is consumed)
+    int n_item = item, n_st = st + 1;
+    if (n_st == spi) n_st = 0, ++n_item;
+    const bool has_next = g + 1 < total;
+    const __nv_bfloat16* np = has_next ? step_ptr(n_item, n_st) : k;
+    const int nj = has_next ? step_key(n_st) : T;  // T: every slot predicated off
+    const int j0 = step_key(st);
+    if (st < nk) {
+      // ---- K step: scores (log2 domain) into smem, running maximum ----
+#pragma unroll
+      for (int u = 0; u < kXU; ++u) {
+        const int j = j0 + 32 * u;
+        float sc = dot8(kv[u], qr);
+        kv[u] = (nj + 32 * u < T) ? ld_stream16(np + u * 32 * 64) : make_uint4(0, 0, 0, 0);
+        sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+        sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+        sc += __shfl_xor_sync(0xffffffffu, sc, 4);
+        if (j < T) {
+          if (sub == 0) s_scores[j] = sc;
+          mx = fmaxf(mx, sc);
+        }
+      }
+      if (st == nk - 1) {  // phase boundary: block maximum (the first V loads are already in flight)
+        mx = warp_max(mx);
+        if (lane == 0) s_redm[warp] = mx;
+        // q is dead from here on: fetch the next item's query so that it is there when its K phase starts
+        if (item + 1 < last) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) qr[i] = q[(long)(item + 1) * 64 + sub * 8 + i] * kScoreScaleLog2;
+        }
+        __syncthreads();
+        m = s_redm[0];
+#pragma unroll
+        for (int w = 1; w < NW; ++w) m = fmaxf(m, s_redm[w]);
+        mx = -INFINITY;
+      }
+    } else {
+      // ---- V step: softmax weights and P.V ----
+#pragma unroll
+      for (int u = 0; u < kXU; ++u) {
+        const int j = j0 + 32 * u;
+        const float pw = j < T ? exp2f(s_scores[j] - m) : 0.f;
+        axpy8(acc, pw, kv[u]);
+        kv[u] = (nj + 32 * u < T) ? ld_stream16(np + u * 32 * 64) : make_uint4(0, 0, 0, 0);
+        if (sub == 0) lsum += pw;
+      }
+      if (st == spi - 1) {  // item done: reduce over key groups and warps, write the head's output
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
+          acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+        }
+        lsum = warp_sum(lsum);
+        if (grp == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) s_acc[warp * 64 + sub * 8 + i] = acc[i];
+        }
+        if (lane == 0) s_redl[warp] = lsum;
+        __syncthreads();
+        if (tid < 64) {
+          float o = 0.f, l = 0.f;
+#pragma unroll
+          for (int w = 0; w < NW; ++w) o += s_acc[w * 64 + tid], l += s_redl[w];
+          out[(long)item * 64 + tid] = __float2bfloat16_rn(o / l);  // out is [B][H*64]
+        }
+        __syncthreads();  // s_acc / s_redl / s_scores are rewritten by the next item
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        lsum = 0.f;
+      }
+    }
+    item = n_item, st = n_st;
+  }
+  pdl_launch_dependents();
+  (void)d;
+}
+
 __global__ void cross_attention_combine_kernel(const float* __restrict__ part_m, const float* __restrict__ part_l,
                                                const float* __restrict__ part_o, __nv_bfloat16* __restrict__ out, int n_head, int n_split) {
   pdl_wait();
@@ -397,6 +528,8 @@ void launch_self_attention_decode(const float* qkv, __nv_bfloat16* k_cache, __nv
 
 int cross_attention_pick_split(int B, int n_head) {
   // enough CTAs for ~4 per SM; a single split once the batch provides them
+  static const int forced = getenv("B200W_CROSS_SPLIT") ? atoi(getenv("B200W_CROSS_SPLIT")) : 0;
+  if (forced > 0) return forced;
   int split = 1;
   while (B * n_head * split < 4 * kNumSMs && split < 8) split *= 2;
   return split;
@@ -404,6 +537,15 @@ int cross_attention_pick_split(int B, int n_head) {
 
 void launch_cross_attention_decode(const float* q, const __nv_bfloat16* k, const __nv_bfloat16* v, __nv_bfloat16* out, int B, int n_head,
                                    int T, int n_split, float* part_m, float* part_l, float* part_o, cudaStream_t stream, bool pdl) {
+  static const bool no_stream = getenv("B200W_NO_CROSS_STREAM") != nullptr;
+  const int n_items = B * n_head;
+  if (!no_stream && n_split == 1 && n_items >= 2 * kNumSMs && T <= kXMaxT) {
+    // single resident wave: at most three CTAs per SM, every CTA the same number of items where the batch allows it
+    const int per = (n_items + 3 * kNumSMs - 1) / (3 * kNumSMs);
+    const int grid = (n_items + per - 1) / per;
+    launch_k(pdl, cross_attention_stream_kernel, dim3(grid), dim3(kCrossThreads), 0, stream, q, k, v, out, n_head, T, n_items, per);
+    return;
+  }
   dim3 grid(n_head * n_split, B);
   launch_k(pdl, cross_attention_decode_kernel, grid, dim3(kCrossThreads), 0, stream, q, k, v, out, n_head, T, n_split, part_m, part_l, part_o);
   if (n_split > 1) launch_pdl(cross_attention_combine_kernel, dim3(n_head, B), dim3(64), 0, stream, part_m, part_l, part_o, out, n_head, n_split);

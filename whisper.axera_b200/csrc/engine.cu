@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <map>
 #include <fstream>
 #include <sstream>
 
@@ -695,6 +696,22 @@ int Engine::run_decode(int B, const std::vector<int>& sot, const DecodeOptions& 
       per_step_launches_[key] = launches_ - before;
       launches_ = before;  // capture does not launch
       CUDA_CHECK(cudaStreamEndCapture(stream_, &g));
+      if (getenv("B200W_DIAG_GRAPH")) {  // diagnostic: launch priorities the captured kernel nodes carry
+        size_t n_nodes = 0;
+        CUDA_CHECK(cudaGraphGetNodes(g, nullptr, &n_nodes));
+        std::vector<cudaGraphNode_t> nodes(n_nodes);
+        CUDA_CHECK(cudaGraphGetNodes(g, nodes.data(), &n_nodes));
+        std::map<int, int> hist;
+        for (cudaGraphNode_t nd : nodes) {
+          cudaGraphNodeType ty;
+          CUDA_CHECK(cudaGraphNodeGetType(nd, &ty));
+          if (ty != cudaGraphNodeTypeKernel) continue;
+          cudaKernelNodeAttrValue v{};
+          CUDA_CHECK(cudaGraphKernelNodeGetAttribute(nd, cudaKernelNodeAttributePriority, &v));
+          hist[v.priority]++;
+        }
+        for (auto& kv : hist) fprintf(stderr, "[b200w] decode graph: %d kernel nodes with priority %d\n", kv.second, kv.first);
+      }
       CUDA_CHECK(cudaGraphInstantiate(&exec, g, 0));
       CUDA_CHECK(cudaGraphDestroy(g));
       graphs_[key] = exec;
