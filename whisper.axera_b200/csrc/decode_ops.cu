@@ -10,6 +10,7 @@
 //   argmax           first maximum (std::max_element, Whisper.cpp:42-45), EOT / loop bookkeeping (:214-222)
 // K/V live in HBM as bf16, head-major [B][H][n][64]: one (sequence, head) is a contiguous 128-byte-per-key stream,
 // read with 16-byte loads (8 lanes per key, 4 keys per warp instruction), fp32 scores / softmax / accumulation.
+#include <algorithm>
 #include <cfloat>
 #include <cstdlib>
 
@@ -324,123 +325,140 @@ constexpr int kXKeysPerStep = (kCrossThreads / 32) * 4 * kXU;  // 256 keys per s
 constexpr int kXMaxT = 1536;
 __global__ void __maxnreg__(64)
 cross_attention_stream_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
-                              __nv_bfloat16* __restrict__ out, int n_head, int T, int n_items, int items_per_cta) {
+                              __nv_bfloat16* __restrict__ out, int T, int n_items, int* __restrict__ work /*[2]: next item, CTAs done*/) {
   constexpr int NW = kCrossThreads / 32;
   __shared__ float s_scores[kXMaxT];
   __shared__ float s_acc[NW * 64];
   __shared__ float s_redm[NW], s_redl[NW];
+  __shared__ int s_item[2];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int grp = lane >> 3, sub = lane & 7;  // 4 keys per warp instruction, 8 lanes (16 B each) per key
-  const int first = blockIdx.x * items_per_cta;
-  const int last = min(n_items, first + items_per_cta);
-  const int d = n_head * 64;
   const int nk = (T + kXKeysPerStep - 1) / kXKeysPerStep;  // steps per phase
   const int spi = 2 * nk;                                  // steps per item
-  const int total = (last - first) * spi;
   const int key0 = warp * 4 + grp;                         // key of slot 0 within a step; slot u adds 32 u
   pdl_wait();
-  if (total <= 0) return;
+  // items ((sequence, head) pairs in the cache's own order) are handed out by an atomic counter: every SM keeps exactly
+  // the CTAs it was given busy until the work runs out, whatever B * H is
+  if (tid == 0) s_item[0] = atomicAdd(&work[0], 1);
+  __syncthreads();
+  int item = s_item[0];
+  int par = 0;
 
   // slot u of step (item, st): tensor K for st < nk else V, key (st % nk) * 256 + 32 u + key0
-  auto step_ptr = [&](int item, int st) {
-    const __nv_bfloat16* base = (st < nk ? k : v) + (long)item * T * 64;  // items are (b, h) pairs = the cache's own order
+  auto step_ptr = [&](int it, int st) {
+    const __nv_bfloat16* base = (st < nk ? k : v) + (long)it * T * 64;
     const int kb = (st < nk ? st : st - nk) * kXKeysPerStep + key0;
     return base + (long)kb * 64 + sub * 8;
   };
   auto step_key = [&](int st) { return (st < nk ? st : st - nk) * kXKeysPerStep + key0; };
 
-  uint4 kv[kXU];
-  {
-    const __nv_bfloat16* p0 = step_ptr(first, 0);
-    const int j0 = step_key(0);
+  if (item < n_items) {
+    uint4 kv[kXU];
+    {
+      const __nv_bfloat16* p0 = step_ptr(item, 0);
+      const int j0 = step_key(0);
 #pragma unroll
-    for (int u = 0; u < kXU; ++u) kv[u] = (j0 + 32 * u < T) ? ld_stream16(p0 + u * 32 * 64) : make_uint4(0, 0, 0, 0);
-  }
-  float qr[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) qr[i] = q[(long)first * 64 + sub * 8 + i] * kScoreScaleLog2;  // q is [B][H*64]: item * 64
-
-  float mx = -INFINITY, m = 0.f, lsum = 0.f;
-  float acc[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  int item = first, st = 0;
-  for (int g = 0; g < total; ++g) {
-    // the step after this one (its loads are issued slot by slot while this step is consumed)
-    int n_item = item, n_st = st + 1;
-    if (n_st == spi) n_st = 0, ++n_item;
-    const bool has_next = g + 1 < total;
-    const __nv_bfloat16* np = has_next ? step_ptr(n_item, n_st) : k;
-    const int nj = has_next ? step_key(n_st) : T;  // T: every slot predicated off
-    const int j0 = step_key(st);
-    if (st < nk) {
-      // ---- K step: scores (log2 domain) into smem, running maximum ----
-#pragma unroll
-      for (int u = 0; u < kXU; ++u) {
-        const int j = j0 + 32 * u;
-        float sc = dot8(kv[u], qr);
-        kv[u] = (nj + 32 * u < T) ? ld_stream16(np + u * 32 * 64) : make_uint4(0, 0, 0, 0);
-        sc += __shfl_xor_sync(0xffffffffu, sc, 1);
-        sc += __shfl_xor_sync(0xffffffffu, sc, 2);
-        sc += __shfl_xor_sync(0xffffffffu, sc, 4);
-        if (j < T) {
-          if (sub == 0) s_scores[j] = sc;
-          mx = fmaxf(mx, sc);
-        }
-      }
-      if (st == nk - 1) {  // phase boundary: block maximum (the first V loads are already in flight)
-        mx = warp_max(mx);
-        if (lane == 0) s_redm[warp] = mx;
-        // q is dead from here on: fetch the next item's query so that it is there when its K phase starts
-        if (item + 1 < last) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) qr[i] = q[(long)(item + 1) * 64 + sub * 8 + i] * kScoreScaleLog2;
-        }
-        __syncthreads();
-        m = s_redm[0];
-#pragma unroll
-        for (int w = 1; w < NW; ++w) m = fmaxf(m, s_redm[w]);
-        mx = -INFINITY;
-      }
-    } else {
-      // ---- V step: softmax weights and P.V ----
-#pragma unroll
-      for (int u = 0; u < kXU; ++u) {
-        const int j = j0 + 32 * u;
-        const float pw = j < T ? exp2f(s_scores[j] - m) : 0.f;
-        axpy8(acc, pw, kv[u]);
-        kv[u] = (nj + 32 * u < T) ? ld_stream16(np + u * 32 * 64) : make_uint4(0, 0, 0, 0);
-        if (sub == 0) lsum += pw;
-      }
-      if (st == spi - 1) {  // item done: reduce over key groups and warps, write the head's output
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
-          acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
-        }
-        lsum = warp_sum(lsum);
-        if (grp == 0) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) s_acc[warp * 64 + sub * 8 + i] = acc[i];
-        }
-        if (lane == 0) s_redl[warp] = lsum;
-        __syncthreads();
-        if (tid < 64) {
-          float o = 0.f, l = 0.f;
-#pragma unroll
-          for (int w = 0; w < NW; ++w) o += s_acc[w * 64 + tid], l += s_redl[w];
-          out[(long)item * 64 + tid] = __float2bfloat16_rn(o / l);  // out is [B][H*64]
-        }
-        __syncthreads();  // s_acc / s_redl / s_scores are rewritten by the next item
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-        lsum = 0.f;
-      }
+      for (int u = 0; u < kXU; ++u) kv[u] = (j0 + 32 * u < T) ? ld_stream16(p0 + u * 32 * 64) : make_uint4(0, 0, 0, 0);
     }
-    item = n_item, st = n_st;
+    float qr[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) qr[i] = q[(long)item * 64 + sub * 8 + i] * kScoreScaleLog2;  // q is [B][H*64]: item * 64
+
+    float mx = -INFINITY, m = 0.f, lsum = 0.f;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    int next_item = n_items;
+    for (;;) {
+      for (int st = 0; st < spi; ++st) {
+        // the step after this one (its loads are issued slot by slot while this step is consumed)
+        const bool same = st + 1 < spi;
+        const bool has_next = same || next_item < n_items;
+        const __nv_bfloat16* np = has_next ? step_ptr(same ? item : next_item, same ? st + 1 : 0) : k;
+        const int nj = has_next ? step_key(same ? st + 1 : 0) : T;  // T: every slot predicated off
+        const int j0 = step_key(st);
+        if (st < nk) {
+          // ---- K step: scores (log2 domain) into smem, running maximum ----
+#pragma unroll
+          for (int u = 0; u < kXU; ++u) {
+            const int j = j0 + 32 * u;
+            float sc = dot8(kv[u], qr);
+            kv[u] = (nj + 32 * u < T) ? ld_stream16(np + u * 32 * 64) : make_uint4(0, 0, 0, 0);
+            sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+            sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+            sc += __shfl_xor_sync(0xffffffffu, sc, 4);
+            if (j < T) {
+              if (sub == 0) s_scores[j] = sc;
+              mx = fmaxf(mx, sc);
+            }
+          }
+          if (st == nk - 1) {  // phase boundary: block maximum (the first V loads are already in flight)
+            mx = warp_max(mx);
+            if (lane == 0) s_redm[warp] = mx;
+            if (tid == 0) s_item[par ^ 1] = atomicAdd(&work[0], 1);  // claim the next item while V streams
+            __syncthreads();
+            m = s_redm[0];
+#pragma unroll
+            for (int w = 1; w < NW; ++w) m = fmaxf(m, s_redm[w]);
+            mx = -INFINITY;
+            next_item = s_item[par ^ 1];
+            // q is dead from here on: fetch the next item's query so that it is there when its K phase starts
+            if (next_item < n_items) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) qr[i] = q[(long)next_item * 64 + sub * 8 + i] * kScoreScaleLog2;
+            }
+          }
+        } else {
+          // ---- V step: softmax weights and P.V ----
+#pragma unroll
+          for (int u = 0; u < kXU; ++u) {
+            const int j = j0 + 32 * u;
+            const float pw = j < T ? exp2f(s_scores[j] - m) : 0.f;
+            axpy8(acc, pw, kv[u]);
+            kv[u] = (nj + 32 * u < T) ? ld_stream16(np + u * 32 * 64) : make_uint4(0, 0, 0, 0);
+            if (sub == 0) lsum += pw;
+          }
+        }
+      }
+      // item done: reduce over key groups and warps, write the head's output (the next item's K loads are in flight)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
+        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+      }
+      lsum = warp_sum(lsum);
+      if (grp == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s_acc[warp * 64 + sub * 8 + i] = acc[i];
+      }
+      if (lane == 0) s_redl[warp] = lsum;
+      __syncthreads();
+      if (tid < 64) {
+        float o = 0.f, l = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) o += s_acc[w * 64 + tid], l += s_redl[w];
+        out[(long)item * 64 + tid] = __float2bfloat16_rn(o / l);  // out is [B][H*64]
+      }
+      __syncthreads();  // s_acc / s_redl / s_scores are rewritten by the next item
+      if (next_item >= n_items) break;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      lsum = 0.f;
+      item = next_item;
+      next_item = n_items;
+      par ^= 1;
+    }
   }
   pdl_launch_dependents();
-  (void)d;
+  // the last CTA to leave re-arms the counters for the next launch (every CTA has made its final claim by then)
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(&work[1], 1) == (int)gridDim.x - 1) {
+      work[0] = 0;
+      work[1] = 0;
+      __threadfence();
+    }
+  }
 }
 
 __global__ void cross_attention_combine_kernel(const float* __restrict__ part_m, const float* __restrict__ part_l,
@@ -536,14 +554,14 @@ int cross_attention_pick_split(int B, int n_head) {
 }
 
 void launch_cross_attention_decode(const float* q, const __nv_bfloat16* k, const __nv_bfloat16* v, __nv_bfloat16* out, int B, int n_head,
-                                   int T, int n_split, float* part_m, float* part_l, float* part_o, cudaStream_t stream, bool pdl) {
+                                   int T, int n_split, float* part_m, float* part_l, float* part_o, cudaStream_t stream, bool pdl, int* work) {
   static const bool no_stream = getenv("B200W_NO_CROSS_STREAM") != nullptr;
   const int n_items = B * n_head;
-  if (!no_stream && n_split == 1 && n_items >= 2 * kNumSMs && T <= kXMaxT) {
-    // single resident wave: at most three CTAs per SM, every CTA the same number of items where the batch allows it
-    const int per = (n_items + 3 * kNumSMs - 1) / (3 * kNumSMs);
-    const int grid = (n_items + per - 1) / per;
-    launch_k(pdl, cross_attention_stream_kernel, dim3(grid), dim3(kCrossThreads), 0, stream, q, k, v, out, n_head, T, n_items, per);
+  if (!no_stream && work != nullptr && n_split == 1 && n_items >= 2 * kNumSMs && T <= kXMaxT) {
+    // single resident wave: three CTAs on every SM, items claimed dynamically
+    static const int ctas_per_sm = getenv("B200W_CROSS_CTAS_PER_SM") ? atoi(getenv("B200W_CROSS_CTAS_PER_SM")) : 3;
+    const int grid = std::min(n_items, ctas_per_sm * kNumSMs);
+    launch_k(pdl, cross_attention_stream_kernel, dim3(grid), dim3(kCrossThreads), 0, stream, q, k, v, out, T, n_items, work);
     return;
   }
   dim3 grid(n_head * n_split, B);
@@ -551,7 +569,13 @@ void launch_cross_attention_decode(const float* q, const __nv_bfloat16* k, const
   if (n_split > 1) launch_pdl(cross_attention_combine_kernel, dim3(n_head, B), dim3(64), 0, stream, part_m, part_l, part_o, out, n_head, n_split);
 }
 
-void decode_ops_set_attributes() {}
+void decode_ops_set_attributes() {
+  // The streaming cross-attention kernel shares its SMs with the tcgen05 GEMM CTAs of the other micro-batch, which need
+  // ~165 KB of shared memory: ask for the shared-memory-heavy L1 split (the kernel bypasses L1 with .nc.L1::no_allocate loads)
+  const char* e = getenv("B200W_CROSS_CARVEOUT");
+  const int carve = e ? atoi(e) : -1;
+  if (carve >= 0) CUDA_CHECK(cudaFuncSetAttribute(cross_attention_stream_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+}
 
 void launch_argmax_finalize(const DecodeState& st, const float* part_val, const int* part_idx, int n_tiles, int part_ld, int B,
                             int n_text_ctx, int eot, int honor_eot, int sot_len, cudaStream_t stream) {

@@ -391,6 +391,8 @@ void Engine::ensure_capacity(int B, long max_samples) {
   part_m_ = dev_alloc<float>(o, np);
   part_l_ = dev_alloc<float>(o, np);
   part_o_ = dev_alloc<float>(o, np * 64);
+  cross_work_ = dev_alloc<int>(o, (size_t)cfg_.l_dec * 4 * 2 + 2);  // item counters of the streaming cross-attention launches
+  CUDA_CHECK(cudaMemset(cross_work_, 0, sizeof(int) * ((size_t)cfg_.l_dec * 4 * 2 + 2)));
   st_.step = dev_alloc<int>(o, 1);
   st_.tokens = dev_alloc<int>(o, (size_t)cap_ * kTextCtx);
   st_.forced = dev_alloc<int>(o, (size_t)cap_ * kTextCtx);
@@ -604,7 +606,8 @@ void Engine::enqueue_decode_step(int B, bool want_logits, bool finalize, int hon
       if (!skip_cross) {
         ScopedLaunchPriority low(0);
         launch_cross_attention_decode(q_dec_ + (size_t)m.b0 * d, cross_k_ + ckv_off, cross_v_ + ckv_off, attn_dec_ + (size_t)m.b0 * d,
-                                      m.nb, H, kAudioCtx, n_split, part_m_ + po, part_l_ + po, part_o_ + po * 64, m.s, /*pdl=*/!chain);
+                                      m.nb, H, kAudioCtx, n_split, part_m_ + po, part_l_ + po, part_o_ + po * 64, m.s, /*pdl=*/!chain,
+                                      cross_work_ + (l * 4 + i) * 2);
       }
       if (chain) CUDA_CHECK(cudaEventRecord(cross_event(l, i), m.s));
       launches_ += 1 + (n_split > 1 ? 1 : 0);
@@ -652,7 +655,7 @@ void Engine::run_cross_attention_only(int B) {
   for (int l = 0; l < cfg_.l_dec; ++l) {
     const size_t ckv_off = (size_t)l * cap_ * H * kAudioCtx * 64;
     launch_cross_attention_decode(q_dec_, cross_k_ + ckv_off, cross_v_ + ckv_off, attn_dec_, B, H, kAudioCtx, n_split, part_m_, part_l_,
-                                  part_o_, stream_);
+                                  part_o_, stream_, true, cross_work_ + (size_t)cfg_.l_dec * 4 * 2);
     launches_ += 1 + (n_split > 1 ? 1 : 0);
   }
 }

@@ -123,6 +123,7 @@ class Engine {
   int device_ = 0;
   cudaStream_t stream_ = nullptr;
   cudaStream_t stream2_ = nullptr;          // second micro-batch of a decoder step
+  int* cross_work_ = nullptr;               // [l_dec][4 micro-batches][2] work counters (+ one pair for time_stage)
   int prio_high_ = 0;                       // most urgent launch priority of the device (cudaDeviceGetStreamPriorityRange)
   std::vector<cudaEvent_t> step_events_;    // fork / join / per-layer cross-attention hand-over
   std::vector<cudaEvent_t> copy_events_;    // per encoder sub-batch: its PCM has been copied (pipelined transcribe())

@@ -133,9 +133,10 @@ void launch_self_attention_decode(const float* qkv, __nv_bfloat16* k_cache, __nv
                                   __nv_bfloat16* out, int B, int n_head, int n_ctx, cudaStream_t stream);
 // cross attention: q f32 [B][d] over bf16 head-major K/V [B][H][T][64]; out bf16 [B][d].
 // part_* are workspaces for the split-T variant ([B*H*n_split] each, o is [..][64]).
+// work: two zero-initialised ints owned by this launch site (large batches: streaming kernel with dynamic item claims).
 void launch_cross_attention_decode(const float* q, const __nv_bfloat16* k, const __nv_bfloat16* v, __nv_bfloat16* out, int B,
                                    int n_head, int T, int n_split, float* part_m, float* part_l, float* part_o,
-                                   cudaStream_t stream, bool pdl = true);
+                                   cudaStream_t stream, bool pdl = true, int* work = nullptr);
 // reduces the argmax partials, applies teacher forcing / EOT bookkeeping, stores the next token
 void launch_advance_step(int* step, cudaStream_t stream, bool pdl = true);  // *step += 1 (once per decoder step)
 void launch_argmax_finalize(const DecodeState& st, const float* part_val, const int* part_idx, int n_tiles, int part_ld, int B,
