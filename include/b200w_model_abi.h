@@ -91,6 +91,8 @@ B200W_API int b200w_time_stage(b200w_engine* e, int stage, int B, int iters, int
 /* Test hooks: tcgen05 GEMM against the SIMT comparator on random data (returns max abs difference), constant tables. */
 B200W_API int b200w_selftest_gemm(int M, int N, int K, int block_n, int epilogue, unsigned seed, float* max_abs_diff, float* max_abs_ref);
 B200W_API int b200w_selftest_attention(int B, int T, int n_head, unsigned seed, float* max_abs_diff, float* max_abs_ref);
+/* decode cross attention: streaming kernel (B * n_head >= 296) vs the per-(sequence, head) kernel, same random inputs */
+B200W_API int b200w_selftest_cross_attention(int B, int n_head, int T, unsigned seed, float* max_abs_diff, float* max_abs_ref);
 B200W_API int b200w_mel_tables(int n_mels, float* bank /*[n_mels][201]*/, float* window /*[400]*/);
 /* Host-logic test hooks (no GPU needed): config parser (Whisper.cpp:93-101), WAV reader (AudioFile.h equivalent; out is
  * [frame][channel]), base64 token decoder (base64.cpp equivalent; returns the decoded length). */

@@ -29,6 +29,9 @@ nvtx.range_pop()
 nvtx.range_push("enc")
 eng.time_stage(1, B, 1)
 nvtx.range_pop()
+nvtx.range_push("xattn")  # the roofline kernel of bench.py: one cross-attention launch per decoder layer over the whole batch
+eng.time_stage(3, B, 1)
+nvtx.range_pop()
 nvtx.range_push("dec")
 eng.time_stage(2, B, 1, n_steps=steps)
 nvtx.range_pop()

@@ -4,9 +4,18 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("B,T,H", [(1, 1500, 2), (2, 1500, 6), (1, 64, 1), (1, 200, 2), (3, 1500, 12)])
+@pytest.mark.parametrize("B,T,H", [(1, 1500, 2), (2, 1500, 6), (1, 64, 1), (1, 200, 2), (3, 1500, 12), (1, 300, 2), (2, 130, 1)])
 def test_attention_matches_comparator(pkg, B, T, H):
     diff, ref = pkg.selftest_attention(B, T, H, seed=B + T + H)
     print("B=%d T=%d H=%d max|diff| %.4g max|ref| %.3g" % (B, T, H, diff, ref))
     assert ref > 0.05
     assert diff <= 2e-2 * max(ref, 1.0)  # both round P and the output to bf16, in different orders
+
+
+# K7 decode cross attention: the streaming kernel (dynamic item claims, rolling loads) against the per-(sequence, head) kernel
+@pytest.mark.parametrize("B,H,T", [(50, 6, 1500), (37, 12, 1500), (128, 12, 1500), (64, 20, 1500), (300, 1, 700), (40, 8, 256)])
+def test_cross_attention_stream_matches_per_head_kernel(pkg, B, H, T):
+    diff, ref = pkg.selftest_cross_attention(B, H, T, seed=B + H + T)
+    print("B=%d H=%d T=%d max|diff| %.4g max|ref| %.3g" % (B, H, T, diff, ref))
+    assert ref > 0.01
+    assert diff <= 1e-2 * max(ref, 1.0)  # same fp32 math, different summation order, bf16 output

@@ -51,7 +51,7 @@ EXPORTED_SYMBOLS = [
     "b200w_last_error", "b200w_engine_create", "b200w_engine_destroy", "b200w_get_dims", "b200w_sot_sequence",
     "b200w_logmel", "b200w_encoder", "b200w_decoder_main", "b200w_decoder_loop", "b200w_greedy", "b200w_transcribe",
     "b200w_upload_pcm", "b200w_transcribe_resident", "b200w_time_stage", "b200w_selftest_gemm", "b200w_mel_tables",
-    "b200w_test_parse_config", "b200w_test_load_wav", "b200w_test_base64", "b200w_selftest_attention",
+    "b200w_test_parse_config", "b200w_test_load_wav", "b200w_test_base64", "b200w_selftest_attention", "b200w_selftest_cross_attention",
 ]
 
 _lib = None
@@ -95,6 +95,7 @@ def load_library():
     lib.b200w_selftest_gemm.argtypes = [ci, ci, ci, ci, ci, ctypes.c_uint, _c_float_p, _c_float_p]
     lib.b200w_mel_tables.argtypes = [ci, _c_float_p, _c_float_p]
     lib.b200w_selftest_attention.argtypes = [ci, ci, ci, ctypes.c_uint, _c_float_p, _c_float_p]
+    lib.b200w_selftest_cross_attention.argtypes = [ci, ci, ci, ctypes.c_uint, _c_float_p, _c_float_p]
     lib.b200w_test_parse_config.argtypes = [cp, cp, ctypes.POINTER(Dims), _c_int_p]
     lib.b200w_test_load_wav.argtypes = [cp, _c_float_p, ci, _c_int_p, _c_int_p, _c_int_p]
     lib.b200w_test_base64.argtypes = [cp, ctypes.c_char_p, ci]
@@ -313,6 +314,14 @@ def selftest_attention(B, T, n_head, seed=0):
     lib = load_library()
     d, r = ctypes.c_float(), ctypes.c_float()
     if lib.b200w_selftest_attention(B, T, n_head, seed, ctypes.byref(d), ctypes.byref(r)) != 0:
+        raise B200Error(lib.b200w_last_error().decode())
+    return d.value, r.value
+
+
+def selftest_cross_attention(B, n_head, T, seed=0):
+    lib = load_library()
+    d, r = ctypes.c_float(), ctypes.c_float()
+    if lib.b200w_selftest_cross_attention(B, n_head, T, seed, ctypes.byref(d), ctypes.byref(r)) != 0:
         raise B200Error(lib.b200w_last_error().decode())
     return d.value, r.value
 

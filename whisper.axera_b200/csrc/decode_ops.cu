@@ -569,13 +569,7 @@ void launch_cross_attention_decode(const float* q, const __nv_bfloat16* k, const
   if (n_split > 1) launch_pdl(cross_attention_combine_kernel, dim3(n_head, B), dim3(64), 0, stream, part_m, part_l, part_o, out, n_head, n_split);
 }
 
-void decode_ops_set_attributes() {
-  // The streaming cross-attention kernel shares its SMs with the tcgen05 GEMM CTAs of the other micro-batch, which need
-  // ~165 KB of shared memory: ask for the shared-memory-heavy L1 split (the kernel bypasses L1 with .nc.L1::no_allocate loads)
-  const char* e = getenv("B200W_CROSS_CARVEOUT");
-  const int carve = e ? atoi(e) : -1;
-  if (carve >= 0) CUDA_CHECK(cudaFuncSetAttribute(cross_attention_stream_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-}
+void decode_ops_set_attributes() {}
 
 void launch_argmax_finalize(const DecodeState& st, const float* part_val, const int* part_idx, int n_tiles, int part_ld, int B,
                             int n_text_ctx, int eot, int honor_eot, int sot_len, cudaStream_t stream) {

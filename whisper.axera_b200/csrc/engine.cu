@@ -602,8 +602,7 @@ void Engine::enqueue_decode_step(int B, bool want_logits, bool finalize, int hon
         if (i == 0 && l > 0) CUDA_CHECK(cudaStreamWaitEvent(m.s, cross_event(l - 1, n_mb - 1), 0));
         if (i > 0) CUDA_CHECK(cudaStreamWaitEvent(m.s, cross_event(l, i - 1), 0));
       }
-      static const bool skip_cross = getenv("B200W_DIAG_SKIP_CROSS") != nullptr;  // timing diagnostic only: results are wrong
-      if (!skip_cross) {
+      {
         ScopedLaunchPriority low(0);
         launch_cross_attention_decode(q_dec_ + (size_t)m.b0 * d, cross_k_ + ckv_off, cross_v_ + ckv_off, attn_dec_ + (size_t)m.b0 * d,
                                       m.nb, H, kAudioCtx, n_split, part_m_ + po, part_l_ + po, part_o_ + po * 64, m.s, /*pdl=*/!chain,

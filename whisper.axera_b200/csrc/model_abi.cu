@@ -326,6 +326,60 @@ int b200w_selftest_attention(int B, int T, int n_head, unsigned seed, float* max
   });
 }
 
+// Decode cross attention: the streaming kernel (large batches) against the one-CTA-per-(sequence, head) kernel on the
+// same random q / K / V.
+int b200w_selftest_cross_attention(int B, int n_head, int T, unsigned seed, float* max_abs_diff, float* max_abs_ref) {
+  if (!max_abs_diff || !max_abs_ref) return -1;
+  return guarded([&] {
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) throw CudaError("no CUDA device");
+    kernels_set_attributes();
+    const int d = n_head * 64;
+    const size_t n_kv = (size_t)B * n_head * T * 64, n_q = (size_t)B * d;
+    std::mt19937 rng(seed);
+    std::normal_distribution<float> nd(0.f, 1.f);
+    std::vector<__nv_bfloat16> hk(n_kv), hv(n_kv);
+    std::vector<float> hq(n_q);
+    for (size_t i = 0; i < n_kv; ++i) hk[i] = __float2bfloat16(nd(rng)), hv[i] = __float2bfloat16(nd(rng));
+    for (size_t i = 0; i < n_q; ++i) hq[i] = nd(rng) * 1.5f;
+    __nv_bfloat16 *dk, *dv, *o1, *o2;
+    float* dq;
+    int* work;
+    CUDA_CHECK(cudaMalloc(&dk, n_kv * 2));
+    CUDA_CHECK(cudaMalloc(&dv, n_kv * 2));
+    CUDA_CHECK(cudaMalloc(&dq, n_q * 4));
+    CUDA_CHECK(cudaMalloc(&o1, n_q * 2));
+    CUDA_CHECK(cudaMalloc(&o2, n_q * 2));
+    CUDA_CHECK(cudaMalloc(&work, 2 * sizeof(int)));
+    CUDA_CHECK(cudaMemcpy(dk, hk.data(), n_kv * 2, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(dv, hv.data(), n_kv * 2, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(dq, hq.data(), n_q * 4, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemset(o1, 0, n_q * 2));
+    CUDA_CHECK(cudaMemset(o2, 0xff, n_q * 2));
+    CUDA_CHECK(cudaMemset(work, 0, 2 * sizeof(int)));
+    cudaStream_t s;
+    CUDA_CHECK(cudaStreamCreate(&s));
+    launch_cross_attention_decode(dq, dk, dv, o1, B, n_head, T, 1, nullptr, nullptr, nullptr, s, false, nullptr);
+    for (int rep = 0; rep < 2; ++rep)  // twice: the second launch runs on the counters the first one re-armed
+      launch_cross_attention_decode(dq, dk, dv, o2, B, n_head, T, 1, nullptr, nullptr, nullptr, s, false, work);
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    std::vector<__nv_bfloat16> a(n_q), b(n_q);
+    CUDA_CHECK(cudaMemcpy(a.data(), o1, n_q * 2, cudaMemcpyDeviceToHost));
+    CUDA_CHECK(cudaMemcpy(b.data(), o2, n_q * 2, cudaMemcpyDeviceToHost));
+    double md = 0, mr = 0;
+    for (size_t i = 0; i < n_q; ++i) {
+      const float x = __bfloat162float(a[i]), y = __bfloat162float(b[i]);
+      if (!(y == y)) md = 1e9;  // NaN (also the 0xff fill of an element the kernel never wrote)
+      md = std::max(md, (double)fabsf(x - y));
+      mr = std::max(mr, (double)fabsf(x));
+    }
+    *max_abs_diff = (float)md;
+    *max_abs_ref = (float)mr;
+    cudaStreamDestroy(s);
+    cudaFree(dk), cudaFree(dv), cudaFree(dq), cudaFree(o1), cudaFree(o2), cudaFree(work);
+  });
+}
+
 // tcgen05 GEMM vs SIMT comparator on random bf16 data.  Epilogues covered here: EPI_BIAS_F32 (2), EPI_BIAS_BF16 (0),
 // EPI_BIAS_GELU_BF16 (1), EPI_BIAS_RESID_F32 (3), EPI_ARGMAX (6).
 int b200w_selftest_gemm(int M, int N, int K, int block_n, int epilogue, unsigned seed, float* max_abs_diff, float* max_abs_ref) {
