@@ -25,6 +25,21 @@ __device__ __forceinline__ uint4 ld_stream16(const void* p) {
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
 }
+// streaming load that marks its L2 lines evict-first: the 0.6 GB a cross-attention launch pulls through L2 is never reused,
+// while the decoder weights the other micro-batch read ~100 us ago are needed again by this one
+__device__ __forceinline__ uint64_t l2_evict_first_policy(bool evict_first) {
+  uint64_t pol, normal;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(normal));
+  return evict_first ? pol : normal;
+}
+__device__ __forceinline__ uint4 ld_stream16_ef(const void* p, uint64_t pol) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p), "l"(pol));
+  return r;
+}
 __device__ __forceinline__ float dot8(const uint4& kv, const float (&q)[8]) {
   float a = bf16lo_to_f32(kv.x) * q[0];
   a = fmaf(bf16hi_to_f32(kv.x), q[1], a);
@@ -325,7 +340,8 @@ constexpr int kXKeysPerStep = (kCrossThreads / 32) * 4 * kXU;  // 256 keys per s
 constexpr int kXMaxT = 1536;
 __global__ void __maxnreg__(64)
 cross_attention_stream_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
-                              __nv_bfloat16* __restrict__ out, int T, int n_items, int* __restrict__ work /*[2]: next item, CTAs done*/) {
+                              __nv_bfloat16* __restrict__ out, int T, int n_items, int* __restrict__ work /*[2]: next item, CTAs done*/,
+                              int evict_first) {
   constexpr int NW = kCrossThreads / 32;
   __shared__ float s_scores[kXMaxT];
   __shared__ float s_acc[NW * 64];
@@ -336,6 +352,7 @@ cross_attention_stream_kernel(const float* __restrict__ q, const __nv_bfloat16* 
   const int nk = (T + kXKeysPerStep - 1) / kXKeysPerStep;  // steps per phase
   const int spi = 2 * nk;                                  // steps per item
   const int key0 = warp * 4 + grp;                         // key of slot 0 within a step; slot u adds 32 u
+  const uint64_t pol = l2_evict_first_policy(evict_first != 0);
   pdl_wait();
   // items ((sequence, head) pairs in the cache's own order) are handed out by an atomic counter: every SM keeps exactly
   // the CTAs it was given busy until the work runs out, whatever B * H is
@@ -358,7 +375,7 @@ cross_attention_stream_kernel(const float* __restrict__ q, const __nv_bfloat16* 
       const __nv_bfloat16* p0 = step_ptr(item, 0);
       const int j0 = step_key(0);
 #pragma unroll
-      for (int u = 0; u < kXU; ++u) kv[u] = (j0 + 32 * u < T) ? ld_stream16(p0 + u * 32 * 64) : make_uint4(0, 0, 0, 0);
+      for (int u = 0; u < kXU; ++u) kv[u] = (j0 + 32 * u < T) ? ld_stream16_ef(p0 + u * 32 * 64, pol) : make_uint4(0, 0, 0, 0);
     }
     float qr[8];
 #pragma unroll
@@ -383,7 +400,7 @@ cross_attention_stream_kernel(const float* __restrict__ q, const __nv_bfloat16* 
           for (int u = 0; u < kXU; ++u) {
             const int j = j0 + 32 * u;
             float sc = dot8(kv[u], qr);
-            kv[u] = (nj + 32 * u < T) ? ld_stream16(np + u * 32 * 64) : make_uint4(0, 0, 0, 0);
+            kv[u] = (nj + 32 * u < T) ? ld_stream16_ef(np + u * 32 * 64, pol) : make_uint4(0, 0, 0, 0);
             sc += __shfl_xor_sync(0xffffffffu, sc, 1);
             sc += __shfl_xor_sync(0xffffffffu, sc, 2);
             sc += __shfl_xor_sync(0xffffffffu, sc, 4);
@@ -415,7 +432,7 @@ cross_attention_stream_kernel(const float* __restrict__ q, const __nv_bfloat16* 
             const int j = j0 + 32 * u;
             const float pw = j < T ? exp2f(s_scores[j] - m) : 0.f;
             axpy8(acc, pw, kv[u]);
-            kv[u] = (nj + 32 * u < T) ? ld_stream16(np + u * 32 * 64) : make_uint4(0, 0, 0, 0);
+            kv[u] = (nj + 32 * u < T) ? ld_stream16_ef(np + u * 32 * 64, pol) : make_uint4(0, 0, 0, 0);
             if (sub == 0) lsum += pw;
           }
         }
@@ -561,7 +578,8 @@ void launch_cross_attention_decode(const float* q, const __nv_bfloat16* k, const
     // single resident wave: three CTAs on every SM, items claimed dynamically
     static const int ctas_per_sm = getenv("B200W_CROSS_CTAS_PER_SM") ? atoi(getenv("B200W_CROSS_CTAS_PER_SM")) : 3;
     const int grid = std::min(n_items, ctas_per_sm * kNumSMs);
-    launch_k(pdl, cross_attention_stream_kernel, dim3(grid), dim3(kCrossThreads), 0, stream, q, k, v, out, T, n_items, work);
+    static const int evict_first = getenv("B200W_NO_EVICT_FIRST") == nullptr;
+    launch_k(pdl, cross_attention_stream_kernel, dim3(grid), dim3(kCrossThreads), 0, stream, q, k, v, out, T, n_items, work, evict_first);
     return;
   }
   dim3 grid(n_head * n_split, B);

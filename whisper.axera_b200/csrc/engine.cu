@@ -176,6 +176,7 @@ Engine::Engine(const std::string& model_root, const std::string& model_type, int
   micro_batch_ = getenv("B200W_NO_MICROBATCH") == nullptr;
   if (const char* e = getenv("B200W_N_MICROBATCH")) n_micro_batch_ = std::max(1, std::min(4, atoi(e)));
   cross_chain_ = getenv("B200W_NO_CROSS_CHAIN") == nullptr;
+  if (const char* e = getenv("B200W_GRAPH_STEPS")) graph_steps_ = std::max(1, std::min(16, atoi(e)));
   for (auto& st : mb_streams_) CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&pinned_flags_), 4096 * sizeof(int)));
 
@@ -393,7 +394,8 @@ void Engine::ensure_capacity(int B, long max_samples) {
   part_o_ = dev_alloc<float>(o, np * 64);
   cross_work_ = dev_alloc<int>(o, (size_t)cfg_.l_dec * 4 * 2 + 2);  // item counters of the streaming cross-attention launches
   CUDA_CHECK(cudaMemset(cross_work_, 0, sizeof(int) * ((size_t)cfg_.l_dec * 4 * 2 + 2)));
-  st_.step = dev_alloc<int>(o, 1);
+  step_ctr_ = dev_alloc<int>(o, 4);  // one step counter per micro-batch (they advance independently inside a graph)
+  st_.step = step_ctr_;
   st_.tokens = dev_alloc<int>(o, (size_t)cap_ * kTextCtx);
   st_.forced = dev_alloc<int>(o, (size_t)cap_ * kTextCtx);
   st_.finished = dev_alloc<int>(o, cap_);
@@ -536,7 +538,7 @@ void Engine::run_encoder_range(int b0, int nb) {
 // micro-batch streams its cross-attention K/V (HBM-bound, all SMs but capped at 3 CTAs each), the other runs its chain of
 // small latency-bound kernels (LayerNorm, M<=128 GEMMs, self attention).  Events hand the HBM "token" back and forth so the
 // two cross-attention kernels alternate instead of competing; sequences are independent, so results do not change.
-void Engine::enqueue_decode_step(int B, bool want_logits, bool finalize, int honor_eot) {
+void Engine::enqueue_decode_step(int B, bool want_logits, bool finalize, int honor_eot, int n_fused) {
   const int d = cfg_.d, H = cfg_.n_head, Ld = cfg_.l_dec;
   int n_mb = (micro_batch_ && B >= 32) ? n_micro_batch_ : 1;
   while (n_mb > 1 && B / n_mb < 16) --n_mb;
@@ -568,10 +570,15 @@ void Engine::enqueue_decode_step(int B, bool want_logits, bool finalize, int hon
     q.use_pdl = 1, q.a_row_offset = m.b0;
     return q;
   };
+  // n_fused consecutive steps in one enqueue (= one CUDA graph): every micro-batch has its own step counter and moves on to
+  // its next step without waiting for the others, so one micro-batch's logits / arg-max / embedding run underneath the other's
+  // cross attention instead of leaving HBM idle at every step boundary
+  for (int fs = 0; fs < n_fused; ++fs) {
   for (int i = 0; i < n_mb; ++i) {
     DecodeState st = st_;
+    st.step = step_ctr_ + i;
     st.tokens += (size_t)mb[i].b0 * kTextCtx;
-    launch_embed(st, emb_f32_, pos_text_, x_dec_ + (size_t)mb[i].b0 * d, mb[i].nb, d, kTextCtx, mb[i].s, /*pdl=*/n_mb == 1);
+    launch_embed(st, emb_f32_, pos_text_, x_dec_ + (size_t)mb[i].b0 * d, mb[i].nb, d, kTextCtx, mb[i].s, /*pdl=*/n_mb == 1 || fs > 0);
   }
   launches_ += n_mb;
   for (int l = 0; l < Ld; ++l) {
@@ -584,7 +591,7 @@ void Engine::enqueue_decode_step(int B, bool want_logits, bool finalize, int hon
       __nv_bfloat16* h = h_dec_ + (size_t)m.b0 * d;
       launch_layernorm(x, L.ln1_g, L.ln1_b, h, m.nb, d, m.s);
       gemm_launch(P.qkv, gp(m, qkv_dec_, 4, 3 * d, 3 * d, L.b_qkv), m.s);
-      launch_self_attention_decode(qkv_dec_ + (size_t)m.b0 * 3 * d, self_k_ + skv_off, self_v_ + skv_off, st_.step,
+      launch_self_attention_decode(qkv_dec_ + (size_t)m.b0 * 3 * d, self_k_ + skv_off, self_v_ + skv_off, step_ctr_ + i,
                                    attn_dec_ + (size_t)m.b0 * d, m.nb, H, kTextCtx, m.s);
       gemm_launch(P.out, gp(m, x_dec_, 4, d, d, L.b_out), m.s);
       launch_layernorm(x, L.lnx_g, L.lnx_b, h, m.nb, d, m.s);
@@ -599,7 +606,7 @@ void Engine::enqueue_decode_step(int B, bool want_logits, bool finalize, int hon
       if (chain) {
         // the cross-attention kernels take turns on HBM: micro-batch i waits for micro-batch i-1's kernel of this layer,
         // micro-batch 0 for the last micro-batch's kernel of the previous layer
-        if (i == 0 && l > 0) CUDA_CHECK(cudaStreamWaitEvent(m.s, cross_event(l - 1, n_mb - 1), 0));
+        if (i == 0 && (l > 0 || fs > 0)) CUDA_CHECK(cudaStreamWaitEvent(m.s, cross_event(l > 0 ? l - 1 : Ld - 1, n_mb - 1), 0));
         if (i > 0) CUDA_CHECK(cudaStreamWaitEvent(m.s, cross_event(l, i - 1), 0));
       }
       {
@@ -632,19 +639,18 @@ void Engine::enqueue_decode_step(int B, bool want_logits, bool finalize, int hon
     launches_ += 2;
     if (finalize) {
       DecodeState st = st_;
+      st.step = step_ctr_ + i;
       st.tokens += (size_t)m.b0 * kTextCtx, st.forced += (size_t)m.b0 * kTextCtx, st.out_tokens += (size_t)m.b0 * kTextCtx;
       st.finished += m.b0;
       launch_argmax_finalize(st, p.part_val, p.part_idx, logits_tiles_, logits_tiles_, m.nb, kTextCtx, cfg_.eot, honor_eot, kSotLen, m.s);
-      launches_ += 1;
+      launch_advance_step(step_ctr_ + i, m.s, /*pdl=*/true);  // this micro-batch's own step counter
+      launches_ += 2;
     }
   }
+  }  // fused steps
   for (int i = 1; i < n_mb; ++i) {
     CUDA_CHECK(cudaEventRecord(step_events_[i], mb[i].s));
     CUDA_CHECK(cudaStreamWaitEvent(stream_, step_events_[i], 0));
-  }
-  if (finalize) {
-    launch_advance_step(st_.step, stream_, /*pdl=*/n_mb == 1);
-    launches_ += 1;
   }
 }
 
@@ -660,7 +666,7 @@ void Engine::run_cross_attention_only(int B) {
 }
 
 void Engine::decode_reset(int B) {
-  CUDA_CHECK(cudaMemsetAsync(st_.step, 0, sizeof(int), stream_));
+  CUDA_CHECK(cudaMemsetAsync(step_ctr_, 0, 4 * sizeof(int), stream_));
   CUDA_CHECK(cudaMemsetAsync(st_.finished, 0, sizeof(int) * B, stream_));
   CUDA_CHECK(cudaMemsetAsync(st_.forced, 0xff, sizeof(int) * (size_t)B * kTextCtx, stream_));  // -1
 }
@@ -686,48 +692,50 @@ int Engine::run_decode(int B, const std::vector<int>& sot, const DecodeOptions& 
   const int n_steps = kSotLen + max_new;  // like the reference, the last token is fed back too and its result discarded
   const bool want_logits = opt.logits_out != nullptr;
   const bool graph = opt.use_graph && !want_logits && getenv("B200W_NO_GRAPH") == nullptr;
-  cudaGraphExec_t exec = nullptr;
-  if (graph) {
-    const int key = B * 2 + (opt.honor_eot ? 1 : 0);
+  // graphs of `k` consecutive decoder steps (k = graph_steps_ and, for the remainder, 1), cached per (B, honor_eot, k)
+  auto get_graph = [&](int k) {
+    const int key = (B * 2 + (opt.honor_eot ? 1 : 0)) * 64 + k;
     auto it = graphs_.find(key);
-    if (it == graphs_.end()) {
-      cudaGraph_t g;
-      CUDA_CHECK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
-      const long before = launches_;
-      enqueue_decode_step(B, false, true, opt.honor_eot ? 1 : 0);
-      per_step_launches_[key] = launches_ - before;
-      launches_ = before;  // capture does not launch
-      CUDA_CHECK(cudaStreamEndCapture(stream_, &g));
-      if (getenv("B200W_DIAG_GRAPH")) {  // diagnostic: launch priorities the captured kernel nodes carry
-        size_t n_nodes = 0;
-        CUDA_CHECK(cudaGraphGetNodes(g, nullptr, &n_nodes));
-        std::vector<cudaGraphNode_t> nodes(n_nodes);
-        CUDA_CHECK(cudaGraphGetNodes(g, nodes.data(), &n_nodes));
-        std::map<int, int> hist;
-        for (cudaGraphNode_t nd : nodes) {
-          cudaGraphNodeType ty;
-          CUDA_CHECK(cudaGraphNodeGetType(nd, &ty));
-          if (ty != cudaGraphNodeTypeKernel) continue;
-          cudaKernelNodeAttrValue v{};
-          CUDA_CHECK(cudaGraphKernelNodeGetAttribute(nd, cudaKernelNodeAttributePriority, &v));
-          hist[v.priority]++;
-        }
-        for (auto& kv : hist) fprintf(stderr, "[b200w] decode graph: %d kernel nodes with priority %d\n", kv.second, kv.first);
+    if (it != graphs_.end()) return std::make_pair(it->second, per_step_launches_[key]);
+    cudaGraph_t g;
+    cudaGraphExec_t exec = nullptr;
+    CUDA_CHECK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+    const long before = launches_;
+    enqueue_decode_step(B, false, true, opt.honor_eot ? 1 : 0, k);
+    per_step_launches_[key] = launches_ - before;
+    launches_ = before;  // capture does not launch
+    CUDA_CHECK(cudaStreamEndCapture(stream_, &g));
+    if (getenv("B200W_DIAG_GRAPH")) {  // diagnostic: launch priorities the captured kernel nodes carry
+      size_t n_nodes = 0;
+      CUDA_CHECK(cudaGraphGetNodes(g, nullptr, &n_nodes));
+      std::vector<cudaGraphNode_t> nodes(n_nodes);
+      CUDA_CHECK(cudaGraphGetNodes(g, nodes.data(), &n_nodes));
+      std::map<int, int> hist;
+      for (cudaGraphNode_t nd : nodes) {
+        cudaGraphNodeType ty;
+        CUDA_CHECK(cudaGraphNodeGetType(nd, &ty));
+        if (ty != cudaGraphNodeTypeKernel) continue;
+        cudaKernelNodeAttrValue v{};
+        CUDA_CHECK(cudaGraphKernelNodeGetAttribute(nd, cudaKernelNodeAttributePriority, &v));
+        hist[v.priority]++;
       }
-      CUDA_CHECK(cudaGraphInstantiate(&exec, g, 0));
-      CUDA_CHECK(cudaGraphDestroy(g));
-      graphs_[key] = exec;
-    } else {
-      exec = it->second;
+      for (auto& kv : hist) fprintf(stderr, "[b200w] decode graph (%d steps): %d kernel nodes with priority %d\n", k, kv.second, kv.first);
     }
-  }
-  const long per_step = graph ? per_step_launches_[B * 2 + (opt.honor_eot ? 1 : 0)] : 0;
+    CUDA_CHECK(cudaGraphInstantiate(&exec, g, 0));
+    CUDA_CHECK(cudaGraphDestroy(g));
+    graphs_[key] = exec;
+    return std::make_pair(exec, per_step_launches_[key]);
+  };
   int steps_done = 0;
-  for (int s = 0; s < n_steps; ++s) {
+  while (steps_done < n_steps) {
+    int k = 1;
     if (graph) {
-      CUDA_CHECK(cudaGraphLaunch(exec, stream_));
-      launches_ += per_step;
+      k = (n_steps - steps_done >= graph_steps_) ? graph_steps_ : 1;
+      const auto ge = get_graph(k);
+      CUDA_CHECK(cudaGraphLaunch(ge.first, stream_));
+      launches_ += ge.second;
     } else {
+      const int s = steps_done;
       enqueue_decode_step(B, want_logits, true, opt.honor_eot ? 1 : 0);
       if (want_logits && s >= kSotLen - 1 && s - (kSotLen - 1) < max_new) {
         // logits after consuming position s = prediction of generated token (s - 3)
@@ -735,8 +743,8 @@ int Engine::run_decode(int B, const std::vector<int>& sot, const DecodeOptions& 
                                      (size_t)vocab_pad_ * 4, (size_t)cfg_.n_vocab * 4, B, cudaMemcpyDeviceToHost, stream_));
       }
     }
-    ++steps_done;
-    if (opt.honor_eot && (s % 16 == 15) && s + 1 < n_steps) {
+    steps_done += k;
+    if (opt.honor_eot && (steps_done % 16 == 0) && steps_done < n_steps) {
       CUDA_CHECK(cudaMemcpyAsync(pinned_flags_, st_.finished, sizeof(int) * std::min(B, 4096), cudaMemcpyDeviceToHost, stream_));
       CUDA_CHECK(cudaStreamSynchronize(stream_));
       bool all = B <= 4096;
@@ -769,7 +777,8 @@ void Engine::decode_step_tokens(int B, const int* tokens_host, int offset, float
   std::vector<int> col(B);
   for (int b = 0; b < B; ++b) col[b] = tokens_host[b];
   CUDA_CHECK(cudaMemcpy2DAsync(st_.tokens + offset, kTextCtx * sizeof(int), col.data(), sizeof(int), sizeof(int), B, cudaMemcpyHostToDevice, stream_));
-  CUDA_CHECK(cudaMemcpyAsync(st_.step, &offset, sizeof(int), cudaMemcpyHostToDevice, stream_));
+  const int offs4[4] = {offset, offset, offset, offset};
+  CUDA_CHECK(cudaMemcpyAsync(step_ctr_, offs4, sizeof(offs4), cudaMemcpyHostToDevice, stream_));
   CUDA_CHECK(cudaStreamSynchronize(stream_));
   enqueue_decode_step(B, true, false, 0);
   if (logits_host)

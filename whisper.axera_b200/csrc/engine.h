@@ -117,12 +117,14 @@ class Engine {
   void load_weights(const std::string& dir, const std::string& type);
   void free_workspace();
   void build_plans();
-  void enqueue_decode_step(int B, bool want_logits, bool finalize, int honor_eot);
+  void enqueue_decode_step(int B, bool want_logits, bool finalize, int honor_eot, int n_fused = 1);
 
   ModelConfig cfg_;
   int device_ = 0;
   cudaStream_t stream_ = nullptr;
   cudaStream_t stream2_ = nullptr;          // second micro-batch of a decoder step
+  int* step_ctr_ = nullptr;                 // [4] decoder position of each micro-batch
+  int graph_steps_ = 8;                     // decoder steps captured per CUDA graph (B200W_GRAPH_STEPS)
   int* cross_work_ = nullptr;               // [l_dec][4 micro-batches][2] work counters (+ one pair for time_stage)
   int prio_high_ = 0;                       // most urgent launch priority of the device (cudaDeviceGetStreamPriorityRange)
   std::vector<cudaEvent_t> step_events_;    // fork / join / per-layer cross-attention hand-over
