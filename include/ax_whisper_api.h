@@ -64,6 +64,13 @@ AX_WHISPER_API int AX_WHISPER_RunPCMTokens(AX_WHISPER_HANDLE handle, const float
  * concatenates the window texts in order.  Windows are independent: no timestamps, no previous-text conditioning. */
 AX_WHISPER_API int AX_WHISPER_RunPCMLong(AX_WHISPER_HANDLE handle, const float* pcm_data, long num_samples, int window_batch, char** result);
 
+/* Concurrency: unlike the reference (whose handle is not re-entrant although whisper_srv calls it from a thread pool,
+ * WhisperHTTPServer.hpp:78), every entry point may be called from several threads on one handle.  AX_WHISPER_RunPCM /
+ * RunFile calls that arrive while a GPU pass is running are coalesced: the next pass transcribes all of them as one batch
+ * (at most B200W_COALESCE_MAX = 64; B200W_COALESCE_WAIT_US adds a fixed wait for company, default 0).
+ * AX_WHISPER_GetStats reports how many single-utterance requests were served in how many GPU passes. */
+AX_WHISPER_API int AX_WHISPER_GetStats(AX_WHISPER_HANDLE handle, long* n_requests, long* n_gpu_passes);
+
 /* Text of the last error on this thread ("" if none). */
 AX_WHISPER_API const char* AX_WHISPER_LastError(void);
 

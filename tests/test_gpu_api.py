@@ -98,3 +98,32 @@ def test_whisper_cli(tmp_path):
     out = subprocess.run([cli, "-w", wav, "-t", "micro", "-p", util.model_root("micro"), "--language", "zh"], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "Result: " in out.stdout and "RTF: " in out.stdout  # whisper_cli.cpp:102-103
+
+
+def test_concurrent_run_pcm_is_coalesced(whisper):
+    """The reference's server calls RunPCM from a thread pool on one non-re-entrant handle (WhisperHTTPServer.hpp:78);
+    here concurrent calls are safe and are transcribed together: same text as one at a time, fewer GPU passes than requests."""
+    import threading
+
+    audios = [util.synth_audio("NUS"[i % 3], 48000 + 1600 * i, 40 + i) for i in range(12)]
+    expect = [whisper.run(a) for a in audios]
+    r0, p0 = whisper.stats()
+    got = [None] * len(audios)
+    errs = []
+
+    def work(i):
+        try:
+            got[i] = whisper.run(audios[i])
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(audios))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errs
+    assert got == expect
+    r1, p1 = whisper.stats()
+    assert r1 - r0 == len(audios)
+    assert p1 - p0 < len(audios), "no coalescing happened: %d passes for %d requests" % (p1 - p0, len(audios))

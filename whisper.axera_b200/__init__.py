@@ -47,7 +47,7 @@ class Times(ctypes.Structure):
 # every symbol include/ax_whisper_api.h and include/b200w_model_abi.h declare
 EXPORTED_SYMBOLS = [
     "AX_WHISPER_Init", "AX_WHISPER_Uninit", "AX_WHISPER_RunFile", "AX_WHISPER_RunPCM", "AX_WHISPER_RunPCMBatch",
-    "AX_WHISPER_RunPCMTokens", "AX_WHISPER_RunPCMLong", "AX_WHISPER_LastError",
+    "AX_WHISPER_RunPCMTokens", "AX_WHISPER_RunPCMLong", "AX_WHISPER_GetStats", "AX_WHISPER_LastError",
     "b200w_last_error", "b200w_engine_create", "b200w_engine_destroy", "b200w_get_dims", "b200w_sot_sequence",
     "b200w_logmel", "b200w_encoder", "b200w_decoder_main", "b200w_decoder_loop", "b200w_greedy", "b200w_transcribe",
     "b200w_upload_pcm", "b200w_transcribe_resident", "b200w_time_stage", "b200w_selftest_gemm", "b200w_mel_tables",
@@ -76,6 +76,7 @@ def load_library():
     lib.AX_WHISPER_RunPCMBatch.argtypes = [vp, ctypes.POINTER(_c_float_p), _c_int_p, ci, ctypes.POINTER(vp)]
     lib.AX_WHISPER_RunPCMTokens.argtypes = [vp, ctypes.POINTER(_c_float_p), _c_int_p, ci, ci, ci, _c_int_p, ci, _c_int_p]
     lib.AX_WHISPER_RunPCMLong.argtypes = [vp, _c_float_p, cl, ci, ctypes.POINTER(vp)]
+    lib.AX_WHISPER_GetStats.argtypes = [vp, ctypes.POINTER(cl), ctypes.POINTER(cl)]
     lib.AX_WHISPER_LastError.restype = cp
     lib.b200w_last_error.restype = cp
     lib.b200w_engine_create.argtypes = [cp, cp, ci, ci, ctypes.POINTER(vp)]
@@ -280,6 +281,12 @@ class Whisper:
         if rc != 0:
             raise B200Error("AX_WHISPER_Run failed: " + self.lib.AX_WHISPER_LastError().decode())
         return self._take(res.value)
+
+    def stats(self):
+        """(single-utterance requests served, GPU passes they took): concurrent run() calls are coalesced into batches."""
+        a, b = ctypes.c_long(), ctypes.c_long()
+        self.lib.AX_WHISPER_GetStats(self.h, ctypes.byref(a), ctypes.byref(b))
+        return a.value, b.value
 
     def run_long(self, audio, window_batch=0):
         """Long-form: consecutive 30 s windows transcribed as one batch, texts concatenated (AX_WHISPER_RunPCMLong)."""

@@ -10,8 +10,13 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <algorithm>
+#include <chrono>
+#include <condition_variable>
+#include <deque>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "engine.h"
@@ -23,11 +28,30 @@ namespace {
 
 thread_local std::string g_api_err;
 
+// One pending AX_WHISPER_RunPCM / RunFile call (the reference serves these one at a time and its handle is not re-entrant,
+// SURVEY.md section 8b "Threading"; its HTTP server calls it from a thread pool regardless).
+struct PendingRequest {
+  const float* pcm = nullptr;
+  int n_samples = 0;
+  std::vector<int> tokens;
+  int rc = 0;
+  std::string err;
+  bool done = false;
+};
+
 struct WhisperHandle {
   std::unique_ptr<Engine> engine;
   std::vector<std::string> token_table;  // base64 text per id (line index = id, Whisper.cpp:123-126)
   std::string lang;
-  std::mutex mu;
+  std::mutex mu;                         // the engine (one GPU pass at a time)
+  // request coalescing: calls that arrive while a pass is running are transcribed together in the next pass
+  std::mutex qmu;
+  std::condition_variable qcv;
+  std::deque<PendingRequest*> queue;
+  bool leader_active = false;
+  int coalesce_max = 64;                 // B200W_COALESCE_MAX
+  int coalesce_wait_us = 0;              // B200W_COALESCE_WAIT_US: extra time a leader waits for company
+  long n_requests = 0, n_passes = 0;
 };
 
 void set_err(const std::string& s) {
@@ -61,6 +85,65 @@ int run_batch(WhisperHandle* h, const float* const* pcm, const int* n_samples, i
   }
 }
 
+// Single-utterance entry: enqueue, then either lead (take everything queued, run one batched pass) or wait for a leader.
+int run_coalesced(WhisperHandle* h, const float* pcm, int n_samples, std::vector<int>* toks) {
+  PendingRequest req;
+  req.pcm = pcm, req.n_samples = n_samples;
+  std::unique_lock<std::mutex> lk(h->qmu);
+  h->queue.push_back(&req);
+  ++h->n_requests;
+  while (!req.done) {
+    if (h->leader_active) {
+      h->qcv.wait(lk);
+      continue;
+    }
+    h->leader_active = true;
+    if (h->coalesce_wait_us > 0) {
+      lk.unlock();
+      std::this_thread::sleep_for(std::chrono::microseconds(h->coalesce_wait_us));
+      lk.lock();
+    }
+    std::vector<PendingRequest*> batch;
+    while (!h->queue.empty() && (int)batch.size() < h->coalesce_max) {
+      batch.push_back(h->queue.front());
+      h->queue.pop_front();
+    }
+    ++h->n_passes;
+    lk.unlock();
+    // requests that cannot be transcribed (too short) fail alone, not the whole pass
+    std::vector<const float*> ptrs;
+    std::vector<int> lens;
+    std::vector<PendingRequest*> ok;
+    for (PendingRequest* r : batch) {
+      if (r->n_samples < 201) {
+        r->rc = -1, r->err = "run whisper failed: audio shorter than 201 samples (reflect padding needs n_fft/2 + 1)";
+      } else {
+        ptrs.push_back(r->pcm), lens.push_back(r->n_samples), ok.push_back(r);
+      }
+    }
+    if (!ok.empty()) {
+      std::vector<std::vector<int>> out;
+      const int rc = run_batch(h, ptrs.data(), lens.data(), (int)ok.size(), DecodeOptions(), &out);
+      for (size_t i = 0; i < ok.size(); ++i) {
+        ok[i]->rc = rc;
+        if (rc == 0) ok[i]->tokens = std::move(out[i]);
+        else ok[i]->err = g_api_err;
+      }
+    }
+    lk.lock();
+    for (PendingRequest* r : batch) r->done = true;
+    h->leader_active = false;
+    h->qcv.notify_all();
+  }
+  lk.unlock();
+  if (req.rc != 0) {
+    if (!req.err.empty()) set_err(req.err);
+    return -1;
+  }
+  *toks = std::move(req.tokens);
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -84,6 +167,8 @@ AX_WHISPER_API AX_WHISPER_HANDLE AX_WHISPER_Init(const char* model_type, const c
     std::string line;
     while (std::getline(fs, line)) h->token_table.push_back(line.substr(0, line.find(' ')));
     h->engine->sot_sequence(language, &h->lang);  // resolves the "unknown language -> zh" fallback once
+    if (const char* e = getenv("B200W_COALESCE_MAX")) h->coalesce_max = std::max(1, atoi(e));
+    if (const char* e = getenv("B200W_COALESCE_WAIT_US")) h->coalesce_wait_us = std::max(0, atoi(e));
     return static_cast<AX_WHISPER_HANDLE>(h.release());
   } catch (const std::exception& ex) {
     set_err(std::string("load models failed: ") + ex.what());
@@ -102,10 +187,9 @@ AX_WHISPER_API int AX_WHISPER_RunPCM(AX_WHISPER_HANDLE handle, float* pcm_data, 
   if (!handle || !pcm_data || !result) return -1;
   *result = nullptr;
   WhisperHandle* h = static_cast<WhisperHandle*>(handle);
-  const float* ptrs[1] = {pcm_data};
-  std::vector<std::vector<int>> toks;
-  if (run_batch(h, ptrs, &num_samples, 1, DecodeOptions(), &toks) != 0) return -1;
-  *result = strdup(detokenize(*h, toks[0]).c_str());
+  std::vector<int> toks;
+  if (run_coalesced(h, pcm_data, num_samples, &toks) != 0) return -1;
+  *result = strdup(detokenize(*h, toks).c_str());
   return *result ? 0 : -1;
 }
 
@@ -165,6 +249,15 @@ AX_WHISPER_API int AX_WHISPER_RunPCMLong(AX_WHISPER_HANDLE handle, const float* 
   }
   *result = strdup(text.c_str());
   return *result ? 0 : -1;
+}
+
+AX_WHISPER_API int AX_WHISPER_GetStats(AX_WHISPER_HANDLE handle, long* n_requests, long* n_gpu_passes) {
+  if (!handle) return -1;
+  WhisperHandle* h = static_cast<WhisperHandle*>(handle);
+  std::lock_guard<std::mutex> lk(h->qmu);
+  if (n_requests) *n_requests = h->n_requests;
+  if (n_gpu_passes) *n_gpu_passes = h->n_passes;
+  return 0;
 }
 
 AX_WHISPER_API int AX_WHISPER_RunPCMTokens(AX_WHISPER_HANDLE handle, const float* const* pcm_data, const int* num_samples, int batch,
