@@ -40,7 +40,9 @@ struct PendingRequest {
 };
 
 struct WhisperHandle {
-  std::unique_ptr<Engine> engine;
+  std::unique_ptr<Engine> engine;                // device 0 of the handle (config, SOT sequence)
+  std::vector<std::unique_ptr<Engine>> extra;    // further devices (B200W_DEVICES): own weights, contexts, streams
+  std::vector<std::unique_ptr<std::mutex>> extra_mu;
   std::vector<std::string> token_table;  // base64 text per id (line index = id, Whisper.cpp:123-126)
   std::string lang;
   std::mutex mu;                         // the engine (one GPU pass at a time)
@@ -70,20 +72,61 @@ std::string detokenize(const WhisperHandle& h, const std::vector<int>& ids) {
   return s;
 }
 
-int run_batch(WhisperHandle* h, const float* const* pcm, const int* n_samples, int B, const DecodeOptions& opt,
-              std::vector<std::vector<int>>* toks) {
+int run_on(Engine* eng, std::mutex* mu, const std::string& lang, const float* const* pcm, const int* n_samples, int B,
+           const DecodeOptions& opt, std::vector<std::vector<int>>* toks, std::string* err) {
   try {
-    std::lock_guard<std::mutex> lock(h->mu);
-    h->engine->transcribe(pcm, n_samples, B, h->lang, opt, toks, nullptr);
+    std::lock_guard<std::mutex> lock(*mu);
+    eng->transcribe(pcm, n_samples, B, lang, opt, toks, nullptr);
     return 0;
   } catch (const std::exception& ex) {
-    set_err(std::string("run whisper failed: ") + ex.what());
+    *err = std::string("run whisper failed: ") + ex.what();
     return -1;
   } catch (...) {
-    set_err("run whisper failed: unknown error");
+    *err = "run whisper failed: unknown error";
     return -1;
   }
 }
+
+// One pass over `B` utterances.  With several devices on the handle the utterances are split into contiguous shards, one
+// host thread per GPU, no data-path collective; token lists come back in utterance order.
+int run_batch(WhisperHandle* h, const float* const* pcm, const int* n_samples, int B, const DecodeOptions& opt,
+              std::vector<std::vector<int>>* toks) {
+  const int n_dev = 1 + (int)h->extra.size();
+  const int G = std::min(n_dev, B);
+  std::string err;
+  if (G <= 1) {
+    const int rc = run_on(h->engine.get(), &h->mu, h->lang, pcm, n_samples, B, opt, toks, &err);
+    if (rc != 0) set_err(err);
+    return rc;
+  }
+  std::vector<std::vector<std::vector<int>>> part(G);
+  std::vector<std::string> errs(G);
+  std::vector<int> rcs(G, 0);
+  std::vector<std::thread> workers;
+  auto shard = [&](int g) { return (int)((long)B * g / G); };
+  for (int g = 0; g < G; ++g) {
+    workers.emplace_back([&, g] {
+      Engine* eng = g == 0 ? h->engine.get() : h->extra[g - 1].get();
+      std::mutex* mu = g == 0 ? &h->mu : h->extra_mu[g - 1].get();
+      const int b0 = shard(g), b1 = shard(g + 1);
+      rcs[g] = run_on(eng, mu, h->lang, pcm + b0, n_samples + b0, b1 - b0, opt, &part[g], &errs[g]);
+    });
+  }
+  for (auto& w : workers) w.join();
+  toks->clear();
+  for (int g = 0; g < G; ++g) {
+    if (rcs[g] != 0) {
+      set_err(errs[g]);
+      return -1;
+    }
+    for (auto& t : part[g]) toks->push_back(std::move(t));
+  }
+  return 0;
+}
+
+}  // namespace
+
+namespace {
 
 // Single-utterance entry: enqueue, then either lead (take everything queued, run one batched pass) or wait for a leader.
 int run_coalesced(WhisperHandle* h, const float* pcm, int n_samples, std::vector<int>* toks) {
@@ -157,7 +200,32 @@ AX_WHISPER_API AX_WHISPER_HANDLE AX_WHISPER_Init(const char* model_type, const c
     std::unique_ptr<WhisperHandle> h(new WhisperHandle());
     const char* dev_env = getenv("B200W_DEVICE");
     const char* mb_env = getenv("B200W_MAX_BATCH");
-    h->engine.reset(new Engine(model_path, model_type, dev_env ? atoi(dev_env) : 0, mb_env ? atoi(mb_env) : 1));
+    // B200W_DEVICES = "all" or "0,2,3": one engine (weights, context, streams) per listed GPU; batches are sharded over them
+    std::vector<int> devices;
+    if (const char* devs = getenv("B200W_DEVICES")) {
+      if (std::string(devs) == "all") {
+        const int n = device_count();
+        for (int i = 0; i < n; ++i) devices.push_back(i);
+      } else {
+        std::string cur;
+        for (const char* c = devs;; ++c) {
+          if (*c == ',' || *c == 0) {
+            if (!cur.empty()) devices.push_back(atoi(cur.c_str()));
+            cur.clear();
+            if (*c == 0) break;
+          } else {
+            cur += *c;
+          }
+        }
+      }
+    }
+    if (devices.empty()) devices.push_back(dev_env ? atoi(dev_env) : 0);
+    const int max_batch = mb_env ? atoi(mb_env) : 1;
+    h->engine.reset(new Engine(model_path, model_type, devices[0], max_batch));
+    for (size_t i = 1; i < devices.size(); ++i) {
+      h->extra.emplace_back(new Engine(model_path, model_type, devices[i], max_batch));
+      h->extra_mu.emplace_back(new std::mutex());
+    }
     const std::string token_path = std::string(model_path) + "/" + model_type + "/" + model_type + "-tokens.txt";
     std::ifstream fs(token_path);
     if (!fs.is_open()) {

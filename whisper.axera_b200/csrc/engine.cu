@@ -193,6 +193,11 @@ Engine::Engine(const std::string& model_root, const std::string& model_type, int
   ensure_capacity(std::max(1, max_batch));
 }
 
+int device_count() {
+  int n = 0;
+  return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
+
 Engine::~Engine() {
   cudaSetDevice(device_);
   cudaStreamSynchronize(stream_);

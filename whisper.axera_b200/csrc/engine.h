@@ -64,6 +64,9 @@ struct StageTimes {
   long kernel_launches = 0;
 };
 
+// number of visible CUDA devices (0 when the driver reports none)
+int device_count();
+
 class Engine {
  public:
   Engine(const std::string& model_root, const std::string& model_type, int device, int max_batch);
