@@ -19,10 +19,15 @@ constexpr int kLnMaxVec = 10;
 
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, int rows, int d) {
+  const int lane = threadIdx.x & 31;
+  // gamma / beta do not depend on the predecessor: pull their lines towards L2 while waiting for it (PDL)
+  if (lane * 32 < d) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(gamma + lane * 32));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(beta + lane * 32));
+  }
   pdl_wait();
   pdl_launch_dependents();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const int nvec = d >> 7;  // float4 per lane (d is a multiple of 128)
   const float4* xr = reinterpret_cast<const float4*>(x + (long)warp * d);

@@ -98,7 +98,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
-  // everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap the previous kernel (PDL)
+  // everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap the previous kernel (PDL), and so may
+  // the first weight tiles: W is constant, only the activations depend on the predecessor.  The producer fills the W half
+  // of the first pipeline stages now and adds the A half after the dependency wait (a decoder-step GEMM is latency-bound:
+  // this takes the HBM round trip of the weights off the dependent chain).
+  int pre_issued = 0;
+  if (warp == 0 && lane == 0 && blockIdx.x < g.total_tiles) {
+    const TileCoord c = tile_coord(blockIdx.x, g);
+    const int n_pre = g.num_k_blocks < kStages ? g.num_k_blocks : kStages;
+    for (int ks = 0; ks < n_pre; ++ks) {
+      const int tap = ks / g.kb_per_tap, kb = ks - tap * g.kb_per_tap;
+      mbar_arrive_expect_tx(&full_bar[ks], Cfg::kStageBytes);
+      tma_load_2d(smem + ks * Cfg::kStageBytes + Cfg::kStageBytesA, &tmap_b, &full_bar[ks], g.w_k0[tap] + kb * BLOCK_K, c.n_blk * BLOCK_N);
+    }
+    pre_issued = n_pre;
+  }
   pdl_wait();
   pdl_launch_dependents();
 
@@ -111,12 +125,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const TileCoord c = tile_coord(t, g);
         for (int tap = 0; tap < g.n_taps; ++tap) {
           for (int kb = 0; kb < g.kb_per_tap; ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
             unsigned char* sa = smem + stage * Cfg::kStageBytes;
             unsigned char* sb = sa + Cfg::kStageBytesA;
-            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            if (pre_issued > 0) {  // first stages of the first tile: the slot is fresh and its W half is already on its way
+              --pre_issued;
+            } else {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+              tma_load_2d(sb, &tmap_b, &full_bar[stage], g.w_k0[tap] + kb * BLOCK_K, c.n_blk * BLOCK_N);
+            }
             tma_load_3d(sa, &tmap_a, &full_bar[stage], g.a_c0[tap] + kb * BLOCK_K, c.m_blk * BLOCK_M + g.a_row[tap] + p.a_row_offset, c.batch + p.a_batch_offset);
-            tma_load_2d(sb, &tmap_b, &full_bar[stage], g.w_k0[tap] + kb * BLOCK_K, c.n_blk * BLOCK_N);
             if (++stage == kStages) {
               stage = 0;
               phase ^= 1;
