@@ -579,79 +579,79 @@ void Engine::enqueue_decode_step(int B, bool want_logits, bool finalize, int hon
   // its next step without waiting for the others, so one micro-batch's logits / arg-max / embedding run underneath the other's
   // cross attention instead of leaving HBM idle at every step boundary
   for (int fs = 0; fs < n_fused; ++fs) {
-  for (int i = 0; i < n_mb; ++i) {
-    DecodeState st = st_;
-    st.step = step_ctr_ + i;
-    st.tokens += (size_t)mb[i].b0 * kTextCtx;
-    launch_embed(st, emb_f32_, pos_text_, x_dec_ + (size_t)mb[i].b0 * d, mb[i].nb, d, kTextCtx, mb[i].s, /*pdl=*/n_mb == 1 || fs > 0);
-  }
-  launches_ += n_mb;
-  for (int l = 0; l < Ld; ++l) {
-    const LayerDec& L = dec_[l];
-    const DecPlans& P = dec_plans_[l];
     for (int i = 0; i < n_mb; ++i) {
-      const MB& m = mb[i];
-      const size_t skv_off = ((size_t)l * cap_ + m.b0) * H * kTextCtx * 64;
-      float* x = x_dec_ + (size_t)m.b0 * d;
-      __nv_bfloat16* h = h_dec_ + (size_t)m.b0 * d;
-      launch_layernorm(x, L.ln1_g, L.ln1_b, h, m.nb, d, m.s);
-      gemm_launch(P.qkv, gp(m, qkv_dec_, 4, 3 * d, 3 * d, L.b_qkv), m.s);
-      launch_self_attention_decode(qkv_dec_ + (size_t)m.b0 * 3 * d, self_k_ + skv_off, self_v_ + skv_off, step_ctr_ + i,
-                                   attn_dec_ + (size_t)m.b0 * d, m.nb, H, kTextCtx, m.s);
-      gemm_launch(P.out, gp(m, x_dec_, 4, d, d, L.b_out), m.s);
-      launch_layernorm(x, L.lnx_g, L.lnx_b, h, m.nb, d, m.s);
-      gemm_launch(P.cq, gp(m, q_dec_, 4, d, d, L.b_cq), m.s);
-    }
-    for (int i = 0; i < n_mb; ++i) {
-      const MB& m = mb[i];
-      const int n_split = cross_attention_pick_split(m.nb, H);
-      const size_t ckv_off = ((size_t)l * cap_ + m.b0) * H * kAudioCtx * 64;
-      const size_t po = (size_t)m.b0 * H * 8;
-      const bool chain = n_mb > 1 && cross_chain_;
-      if (chain) {
-        // the cross-attention kernels take turns on HBM: micro-batch i waits for micro-batch i-1's kernel of this layer,
-        // micro-batch 0 for the last micro-batch's kernel of the previous layer
-        if (i == 0 && (l > 0 || fs > 0)) CUDA_CHECK(cudaStreamWaitEvent(m.s, cross_event(l > 0 ? l - 1 : Ld - 1, n_mb - 1), 0));
-        if (i > 0) CUDA_CHECK(cudaStreamWaitEvent(m.s, cross_event(l, i - 1), 0));
-      }
-      {
-        ScopedLaunchPriority low(0);
-        launch_cross_attention_decode(q_dec_ + (size_t)m.b0 * d, cross_k_ + ckv_off, cross_v_ + ckv_off, attn_dec_ + (size_t)m.b0 * d,
-                                      m.nb, H, kAudioCtx, n_split, part_m_ + po, part_l_ + po, part_o_ + po * 64, m.s, /*pdl=*/!chain,
-                                      cross_work_ + (l * 4 + i) * 2);
-      }
-      if (chain) CUDA_CHECK(cudaEventRecord(cross_event(l, i), m.s));
-      launches_ += 1 + (n_split > 1 ? 1 : 0);
-    }
-    for (int i = 0; i < n_mb; ++i) {
-      const MB& m = mb[i];
-      float* x = x_dec_ + (size_t)m.b0 * d;
-      __nv_bfloat16* h = h_dec_ + (size_t)m.b0 * d;
-      gemm_launch(P.co, gp(m, x_dec_, 4, d, d, L.b_co), m.s);
-      launch_layernorm(x, L.ln2_g, L.ln2_b, h, m.nb, d, m.s);
-      gemm_launch(P.fc1, gp(m, mlp_dec_, 2, 4 * d, 4 * d, L.b_fc1), m.s);
-      gemm_launch(P.fc2, gp(m, x_dec_, 4, d, d, L.b_fc2), m.s);
-    }
-    launches_ += 10 * n_mb;
-  }
-  for (int i = 0; i < n_mb; ++i) {
-    const MB& m = mb[i];
-    launch_layernorm(x_dec_ + (size_t)m.b0 * d, dec_ln_g_, dec_ln_b_, h_dec_ + (size_t)m.b0 * d, m.nb, d, m.s);
-    GemmParams p = gp(m, want_logits ? logits_ : nullptr, 4, vocab_pad_, cfg_.n_vocab, nullptr);
-    if (!want_logits) p.out = nullptr;
-    p.part_val = part_val_ + (size_t)m.b0 * logits_tiles_, p.part_idx = part_idx_ + (size_t)m.b0 * logits_tiles_, p.part_ld = logits_tiles_;
-    gemm_launch(p_logits_, p, m.s);
-    launches_ += 2;
-    if (finalize) {
       DecodeState st = st_;
       st.step = step_ctr_ + i;
-      st.tokens += (size_t)m.b0 * kTextCtx, st.forced += (size_t)m.b0 * kTextCtx, st.out_tokens += (size_t)m.b0 * kTextCtx;
-      st.finished += m.b0;
-      launch_argmax_finalize(st, p.part_val, p.part_idx, logits_tiles_, logits_tiles_, m.nb, kTextCtx, cfg_.eot, honor_eot, kSotLen, m.s);
-      launch_advance_step(step_ctr_ + i, m.s, /*pdl=*/true);  // this micro-batch's own step counter
-      launches_ += 2;
+      st.tokens += (size_t)mb[i].b0 * kTextCtx;
+      launch_embed(st, emb_f32_, pos_text_, x_dec_ + (size_t)mb[i].b0 * d, mb[i].nb, d, kTextCtx, mb[i].s, /*pdl=*/n_mb == 1 || fs > 0);
     }
-  }
+    launches_ += n_mb;
+    for (int l = 0; l < Ld; ++l) {
+      const LayerDec& L = dec_[l];
+      const DecPlans& P = dec_plans_[l];
+      for (int i = 0; i < n_mb; ++i) {
+        const MB& m = mb[i];
+        const size_t skv_off = ((size_t)l * cap_ + m.b0) * H * kTextCtx * 64;
+        float* x = x_dec_ + (size_t)m.b0 * d;
+        __nv_bfloat16* h = h_dec_ + (size_t)m.b0 * d;
+        launch_layernorm(x, L.ln1_g, L.ln1_b, h, m.nb, d, m.s);
+        gemm_launch(P.qkv, gp(m, qkv_dec_, 4, 3 * d, 3 * d, L.b_qkv), m.s);
+        launch_self_attention_decode(qkv_dec_ + (size_t)m.b0 * 3 * d, self_k_ + skv_off, self_v_ + skv_off, step_ctr_ + i,
+                                     attn_dec_ + (size_t)m.b0 * d, m.nb, H, kTextCtx, m.s);
+        gemm_launch(P.out, gp(m, x_dec_, 4, d, d, L.b_out), m.s);
+        launch_layernorm(x, L.lnx_g, L.lnx_b, h, m.nb, d, m.s);
+        gemm_launch(P.cq, gp(m, q_dec_, 4, d, d, L.b_cq), m.s);
+      }
+      for (int i = 0; i < n_mb; ++i) {
+        const MB& m = mb[i];
+        const int n_split = cross_attention_pick_split(m.nb, H);
+        const size_t ckv_off = ((size_t)l * cap_ + m.b0) * H * kAudioCtx * 64;
+        const size_t po = (size_t)m.b0 * H * 8;
+        const bool chain = n_mb > 1 && cross_chain_;
+        if (chain) {
+          // the cross-attention kernels take turns on HBM: micro-batch i waits for micro-batch i-1's kernel of this layer,
+          // micro-batch 0 for the last micro-batch's kernel of the previous layer
+          if (i == 0 && (l > 0 || fs > 0)) CUDA_CHECK(cudaStreamWaitEvent(m.s, cross_event(l > 0 ? l - 1 : Ld - 1, n_mb - 1), 0));
+          if (i > 0) CUDA_CHECK(cudaStreamWaitEvent(m.s, cross_event(l, i - 1), 0));
+        }
+        {
+          ScopedLaunchPriority low(0);
+          launch_cross_attention_decode(q_dec_ + (size_t)m.b0 * d, cross_k_ + ckv_off, cross_v_ + ckv_off, attn_dec_ + (size_t)m.b0 * d,
+                                        m.nb, H, kAudioCtx, n_split, part_m_ + po, part_l_ + po, part_o_ + po * 64, m.s, /*pdl=*/!chain,
+                                        cross_work_ + (l * 4 + i) * 2);
+        }
+        if (chain) CUDA_CHECK(cudaEventRecord(cross_event(l, i), m.s));
+        launches_ += 1 + (n_split > 1 ? 1 : 0);
+      }
+      for (int i = 0; i < n_mb; ++i) {
+        const MB& m = mb[i];
+        float* x = x_dec_ + (size_t)m.b0 * d;
+        __nv_bfloat16* h = h_dec_ + (size_t)m.b0 * d;
+        gemm_launch(P.co, gp(m, x_dec_, 4, d, d, L.b_co), m.s);
+        launch_layernorm(x, L.ln2_g, L.ln2_b, h, m.nb, d, m.s);
+        gemm_launch(P.fc1, gp(m, mlp_dec_, 2, 4 * d, 4 * d, L.b_fc1), m.s);
+        gemm_launch(P.fc2, gp(m, x_dec_, 4, d, d, L.b_fc2), m.s);
+      }
+      launches_ += 10 * n_mb;
+    }
+    for (int i = 0; i < n_mb; ++i) {
+      const MB& m = mb[i];
+      launch_layernorm(x_dec_ + (size_t)m.b0 * d, dec_ln_g_, dec_ln_b_, h_dec_ + (size_t)m.b0 * d, m.nb, d, m.s);
+      GemmParams p = gp(m, want_logits ? logits_ : nullptr, 4, vocab_pad_, cfg_.n_vocab, nullptr);
+      if (!want_logits) p.out = nullptr;
+      p.part_val = part_val_ + (size_t)m.b0 * logits_tiles_, p.part_idx = part_idx_ + (size_t)m.b0 * logits_tiles_, p.part_ld = logits_tiles_;
+      gemm_launch(p_logits_, p, m.s);
+      launches_ += 2;
+      if (finalize) {
+        DecodeState st = st_;
+        st.step = step_ctr_ + i;
+        st.tokens += (size_t)m.b0 * kTextCtx, st.forced += (size_t)m.b0 * kTextCtx, st.out_tokens += (size_t)m.b0 * kTextCtx;
+        st.finished += m.b0;
+        launch_argmax_finalize(st, p.part_val, p.part_idx, logits_tiles_, logits_tiles_, m.nb, kTextCtx, cfg_.eot, honor_eot, kSotLen, m.s);
+        launch_advance_step(step_ctr_ + i, m.s, /*pdl=*/true);  // this micro-batch's own step counter
+        launches_ += 2;
+      }
+    }
   }  // fused steps
   for (int i = 1; i < n_mb; ++i) {
     CUDA_CHECK(cudaEventRecord(step_events_[i], mb[i].s));
