@@ -539,10 +539,11 @@ void Engine::run_encoder_range(int b0, int nb) {
   }
 }
 
-// One decoder step for B sequences.  With B >= 32 the batch is split into two micro-batches on two streams: while one
-// micro-batch streams its cross-attention K/V (HBM-bound, all SMs but capped at 3 CTAs each), the other runs its chain of
-// small latency-bound kernels (LayerNorm, M<=128 GEMMs, self attention).  Events hand the HBM "token" back and forth so the
-// two cross-attention kernels alternate instead of competing; sequences are independent, so results do not change.
+// n_fused decoder steps for B sequences.  With B >= 32 the batch is split into two micro-batches on two streams: while one
+// micro-batch streams its cross-attention K/V (HBM-bound; a single resident wave of 3 CTAs per SM that leaves registers and
+// shared memory for others), the other runs its chain of short latency-bound kernels (LayerNorm, M <= 128 GEMMs, self
+// attention) on the same SMs.  Events hand the HBM "token" back and forth so the cross-attention kernels alternate instead
+// of competing; sequences are independent, so results do not change.
 void Engine::enqueue_decode_step(int B, bool want_logits, bool finalize, int honor_eot, int n_fused) {
   const int d = cfg_.d, H = cfg_.n_head, Ld = cfg_.l_dec;
   int n_mb = (micro_batch_ && B >= 32) ? n_micro_batch_ : 1;

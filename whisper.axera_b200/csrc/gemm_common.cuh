@@ -27,7 +27,7 @@ struct GemmGeom {
 
 // Epilogue of one accumulator tile, executed by all kEpiWarps epilogue warps of a CTA (epi_warp = 0..kEpiWarps-1, its
 // TMEM lane group is tmem_lane_group = (hardware warp id) % 4).  tmem_acc = TMEM column base of the accumulator stage.
-// Waits on tmem_full_bar itself (after staging the bias and prefetching the first residual chunk).
+// Waits on tmem_full_bar itself (after staging the bias and prefetching the first positional-embedding chunk).
 template <int BLOCK_N, int EPI, int kEpiWarps>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const TileCoord& c, uint32_t tmem_acc, float* sb, uint64_t* tmem_full_bar,
                                               uint32_t acc_phase, int epi_warp, int lg, int lane) {

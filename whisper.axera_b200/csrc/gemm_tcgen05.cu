@@ -7,14 +7,19 @@
 // time windows, attention / MLP projections of the encoder blocks :177-178, cross K/V projections :205-210,
 // every Linear of the decoder step :245-247,:228-230,:298 and the tied logits product :378-385).
 //
-// Structure (one CTA per SM, persistent over output tiles, 2 + 8 warps):
-//   warp 0  (1 lane)  TMA producer: A tile 128x64 and W tile BLOCK_Nx64 per k-block, SWIZZLE_128B, kStages ring
+// This file is the single-CTA kernel: the decoder-step GEMMs (M = micro-batch <= 128 rows, BLOCK_N = 32, one tile per CTA,
+// 192 threads x 72 registers so that a CTA fits next to the resident cross-attention CTAs of the other micro-batch), the
+// logits GEMM (BLOCK_N = 128, fused arg-max) and the comparator / fallback for the encoder, whose large GEMMs run on the
+// CTA-pair kernel of gemm2cta_tcgen05.cu.
+// Structure (persistent over output tiles, 2 + 4 warps for BLOCK_N < 128, 2 + 8 otherwise):
+//   warp 0  (1 lane)  TMA producer: A tile 128x64 and W tile BLOCK_Nx64 per k-block, SWIZZLE_128B, kStages ring; the W
+//                     halves of the first stages are issued before the programmatic-dependent-launch wait
 //   warp 1  (1 lane)  MMA issuer: 4 x tcgen05.mma (M=128, N=BLOCK_N, K=16) per k-block into one of two TMEM
 //                     accumulator stages; tcgen05.commit releases smem slots / publishes the accumulator
-//   warps 2-9         epilogue: tcgen05.ld 32 columns at a time (thread = output row; two warps per TMEM lane group
-//                     split the columns), software-pipelined against the next chunk's TMEM read and residual loads,
-//                     bias staged in smem; fused bias / GELU / residual / positional embedding / head-major scatter /
-//                     arg-max, direct 16-byte stores
+//   other warps       epilogue: tcgen05.ld 32 columns at a time (thread = output row; with 8 warps two warps per TMEM lane
+//                     group split the columns), software-pipelined against the next chunk's TMEM read, bias staged in
+//                     smem; fused bias / GELU / positional embedding / head-major scatter / arg-max with direct 16-byte
+//                     stores, residual update as a vector reduction at L2 (red.global.add.v4.f32)
 // Tile order is n-fastest so the CTAs in flight share A row-blocks and the whole W through L2.
 #include <cfloat>
 #include <mutex>
