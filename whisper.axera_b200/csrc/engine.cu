@@ -176,6 +176,7 @@ Engine::Engine(const std::string& model_root, const std::string& model_type, int
   micro_batch_ = getenv("B200W_NO_MICROBATCH") == nullptr;
   if (const char* e = getenv("B200W_N_MICROBATCH")) n_micro_batch_ = std::max(1, std::min(4, atoi(e)));
   cross_chain_ = getenv("B200W_NO_CROSS_CHAIN") == nullptr;
+  cross_chain_forced_ = getenv("B200W_CROSS_CHAIN") != nullptr;
   if (const char* e = getenv("B200W_GRAPH_STEPS")) graph_steps_ = std::max(1, std::min(16, atoi(e)));
   for (auto& st : mb_streams_) CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&pinned_flags_), 4096 * sizeof(int)));
@@ -570,6 +571,10 @@ void Engine::enqueue_decode_step(int B, bool want_logits, bool finalize, int hon
     CUDA_CHECK(cudaEventRecord(ev_fork, stream_));
     for (int i = 1; i < n_mb; ++i) CUDA_CHECK(cudaStreamWaitEvent(mb[i].s, ev_fork, 0));
   }
+  // hand-over events between the cross-attention kernels only pay off when a launch is long against the chain it has to
+  // cover (measured: small B=256, 590 MB per launch: +2 % with; base B=64, 98 MB: -5 % with; turbo B=128 / base B=256: neutral);
+  // decided once per step from the largest micro-batch so that every micro-batch takes part or none does
+  const bool chain = n_mb > 1 && cross_chain_ && (cross_chain_forced_ || (size_t)mb[0].nb * kAudioCtx * d * 4 >= ((size_t)512 << 20));
   auto gp = [&](const MB& m, void* out, size_t elem, long ldo, int N, const float* bias) {
     GemmParams q{};
     q.rows_valid = m.nb, q.N = N, q.out = static_cast<char*>(out) + (size_t)m.b0 * ldo * elem, q.ldo = ldo, q.bias = bias, q.n_batch = 1;
@@ -608,7 +613,6 @@ void Engine::enqueue_decode_step(int B, bool want_logits, bool finalize, int hon
         const int n_split = cross_attention_pick_split(m.nb, H);
         const size_t ckv_off = ((size_t)l * cap_ + m.b0) * H * kAudioCtx * 64;
         const size_t po = (size_t)m.b0 * H * 8;
-        const bool chain = n_mb > 1 && cross_chain_;
         if (chain) {
           // the cross-attention kernels take turns on HBM: micro-batch i waits for micro-batch i-1's kernel of this layer,
           // micro-batch 0 for the last micro-batch's kernel of the previous layer

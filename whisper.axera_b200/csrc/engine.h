@@ -134,6 +134,7 @@ class Engine {
   std::vector<cudaEvent_t> copy_events_;    // per encoder sub-batch: its PCM has been copied (pipelined transcribe())
   bool micro_batch_ = true;
   int n_micro_batch_ = 2;                   // micro-batches of a decoder step (B200W_N_MICROBATCH, 1..4)
+  bool cross_chain_forced_ = false;         // B200W_CROSS_CHAIN: hand over regardless of the launch size
   bool cross_chain_ = true;                 // hand the cross-attention kernels over micro-batch to micro-batch with events
   cudaStream_t mb_streams_[2] = {nullptr, nullptr};  // streams of micro-batches 2 and 3
   int cap_ = 0;
