@@ -31,7 +31,7 @@ namespace b200w {
 
 namespace {
 
-constexpr int kFramesPerCta = 32;
+constexpr int kFramesPerCta = 16;
 constexpr int kThreads = 256;
 constexpr int kNfft = 400;
 constexpr int kHop = 160;
