@@ -31,12 +31,12 @@ namespace b200w {
 
 namespace {
 
-constexpr int kFramesPerCta = 16;
+constexpr int kFramesPerCta = 8;  // 32 KB of smem per CTA -> 7 CTAs per SM (32 frames: 2 CTAs, 2.42 ms per 256 chunks; 8: 1.59 ms)
 constexpr int kThreads = 256;
 constexpr int kNfft = 400;
 constexpr int kHop = 160;
 constexpr int kBins = 201;
-constexpr int kPcmTile = kHop * (kFramesPerCta - 1) + kNfft;  // 5360 samples cover 32 frames
+constexpr int kPcmTile = kHop * (kFramesPerCta - 1) + kNfft;  // samples covered by the CTA's frames
 constexpr int kOutFrames = 3000;
 
 struct MelTablesDev {
@@ -106,7 +106,7 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
     atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
 }
 
-// pass 1: one CTA = 32 consecutive STFT frames of one utterance
+// pass 1: one CTA = kFramesPerCta consecutive STFT frames of one utterance
 __global__ void __launch_bounds__(kThreads) logmel_frames_kernel(const float* __restrict__ pcm, long pcm_stride,
                                                                 const int* __restrict__ n_samples_arr, int n_mels,
                                                                 int bank, float* __restrict__ out,
@@ -255,7 +255,7 @@ __global__ void logmel_init_max_kernel(float* utt_max, int B) {
   if (i < B) utt_max[i] = -FLT_MAX;  // Whisper.cpp:158
 }
 
-// pass 2: in-place normalisation of a [n_mels x 32 frames] tile + bf16 time-major copy for conv1.
+// pass 2: in-place normalisation of a [n_mels x kFramesPerCta frames] tile + bf16 time-major copy for conv1.
 // (max(L, float(mmax - 8.0)) + 4.0) / 4.0 is evaluated in double by the reference (Whisper.cpp:171); L + 4 is
 // exact in double and /4 is a power-of-two scaling, so the float result equals fl32(L + 4) * 0.25 exactly.
 __global__ void __launch_bounds__(kThreads) logmel_normalize_kernel(float* __restrict__ out, const float* __restrict__ utt_max,
