@@ -60,8 +60,16 @@ def special_tokens(n_vocab):
     return t
 
 
-def make_config(arch):
-    a = ARCHS[arch]
+def dims_from_weights(W):
+    """Architecture constants of a state dict in openai-whisper naming (head_dim is 64 in every Whisper release)."""
+    d = int(W["encoder.conv1.weight"].shape[0])
+    n_layers = lambda prefix: 1 + max(int(k.split(".")[2]) for k in W if k.startswith(prefix + ".blocks."))
+    return dict(n_mels=int(W["encoder.conv1.weight"].shape[1]), d=d, heads=d // 64, l_enc=n_layers("encoder"),
+                l_dec=n_layers("decoder"), n_vocab=int(W["decoder.token_embedding.weight"].shape[0]))
+
+
+def make_config(arch, dims=None):
+    a = dims if dims is not None else ARCHS[arch]
     st = special_tokens(a["n_vocab"])
     codes = LANG_CODES[: st["n_lang"]]
     lang_tokens = [st["sot"] + 1 + i for i in range(st["n_lang"])]
@@ -206,15 +214,18 @@ def write_tokens(path, tiktoken_path=None, n=50257):
 
 
 def build_model_dir(root, arch, seed=None, tiktoken_path=None, weights=None):
+    """weights: optional state dict (openai-whisper names, fp32 numpy); `arch` is then only the directory / file prefix and
+    the configuration is derived from the tensor shapes (tools/convert_checkpoint.py)."""
     d = os.path.join(root, arch)
     os.makedirs(d, exist_ok=True)
     W = weights if weights is not None else init_weights(arch, seed)
+    dims = dims_from_weights(W) if (weights is not None and arch not in ARCHS) else None
     enc = {k: v for k, v in W.items() if is_encoder_file_tensor(k)}
     dec = {k: v for k, v in W.items() if not is_encoder_file_tensor(k)}
     write_b200w(os.path.join(d, "%s-encoder.b200w" % arch), enc)
     write_b200w(os.path.join(d, "%s-decoder.b200w" % arch), dec)
     with open(os.path.join(d, "%s_config.json" % arch), "w") as f:
-        json.dump(make_config(arch), f, indent=4)
+        json.dump(make_config(arch, dims), f, indent=4)
     write_tokens(os.path.join(d, "%s-tokens.txt" % arch), tiktoken_path)
     return d
 
