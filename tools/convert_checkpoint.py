@@ -75,6 +75,8 @@ def check(W):
     dims = make_model.dims_from_weights(W)
     if dims["d"] % 128 or dims["d"] > 1280:
         raise SystemExit("d_model %d: the engine's kernels cover multiples of 128 up to 1280" % dims["d"])
+    if dims["n_vocab"] not in (51865, 51866):
+        raise SystemExit("n_vocab %d: only the multilingual vocabularies (51865, 51866) have a special-token table here" % dims["n_vocab"])
     if W["decoder.positional_embedding"].shape[0] != make_model.N_TEXT_CTX:
         raise SystemExit("n_text_ctx must be 448")
     return dims
