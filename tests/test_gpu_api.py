@@ -100,6 +100,21 @@ def test_whisper_cli(tmp_path):
     assert "Result: " in out.stdout and "RTF: " in out.stdout  # whisper_cli.cpp:102-103
 
 
+def test_whisper_cli_long_form(whisper, tmp_path):
+    # --long (extension): every 30 s window of the file, same text as AX_WHISPER_RunPCMLong on the same samples
+    a = np.concatenate([util.synth_audio("S", 480000, 21), util.synth_audio("N", 480000, 22), util.synth_audio("U", 90000, 23)])
+    wav = str(tmp_path / "long.wav")
+    _write_wav(wav, a)
+    pcm16 = (np.clip(a, -1, 1) * 32767).astype("<i2").astype(np.float32) / 32768.0  # what the WAV reader hands to the engine
+    expect = whisper.run_long(pcm16)
+    cli = os.path.join(util.ROOT, "whisper.axera_b200", "whisper_cli")
+    out = subprocess.run([cli, "-w", wav, "-t", "micro", "-p", util.model_root("micro"), "--long"], capture_output=True, text=True, timeout=180)
+    assert out.returncode == 0, out.stdout + out.stderr
+    line = [l for l in out.stdout.splitlines() if l.startswith("Result: ")][0]
+    assert line[len("Result: "):] == expect
+    assert len(expect) > 0
+
+
 def test_concurrent_run_pcm_is_coalesced(whisper):
     """The reference's server calls RunPCM from a thread pool on one non-re-entrant handle (WhisperHTTPServer.hpp:78);
     here concurrent calls are safe and are transcribed together: same text as one at a time, fewer GPU passes than requests."""

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "../../include/ax_whisper_api.h"
 #include "host_utils.h"
@@ -19,14 +20,20 @@ static void usage(const char* argv0) {
           "  -t, --model_type    tiny, base, small, turbo, large (string [=turbo])\n"
           "  -p, --model_path    model path which contains tiny/ base/ small/ turbo/ (string [=../models-b200])\n"
           "      --language      en, zh (string [=zh])\n"
+          "      --long          transcribe the whole file in 30 s windows (extension; the reference stops after 30 s)\n"
           "  -?, --help          print this message\n",
           argv0);
 }
 
 int main(int argc, char** argv) {
   std::string wav_file, model_type = "turbo", model_path = "../models-b200", language = "zh";
+  bool long_form = false;
   for (int i = 1; i < argc; ++i) {
     std::string a = argv[i];
+    if (a == "--long") {
+      long_form = true;
+      continue;
+    }
     auto value = [&](const char* long_name, const char* short_name, std::string* dst) {
       const std::string ln = std::string("--") + long_name;
       if (a.rfind(ln + "=", 0) == 0) {
@@ -78,7 +85,16 @@ int main(int argc, char** argv) {
 
   t0 = std::chrono::steady_clock::now();
   char* result = nullptr;
-  if (0 != AX_WHISPER_RunFile(handle, wav_file.c_str(), &result)) {
+  int rc;
+  if (long_form) {  // same channel handling as RunFile (ax_whisper_api.cpp:105-113), every 30 s window instead of the first
+    std::vector<float>& s = wav.channels[0];
+    if (wav.channels.size() == 2)
+      for (size_t i = 0; i < s.size(); ++i) s[i] = (s[i] + wav.channels[1][i]) / 2;
+    rc = AX_WHISPER_RunPCMLong(handle, s.data(), (long)s.size(), 0, &result);
+  } else {
+    rc = AX_WHISPER_RunFile(handle, wav_file.c_str(), &result);
+  }
+  if (0 != rc) {
     printf("AX_WHISPER_Run failed!\n");
     AX_WHISPER_Uninit(handle);
     return -1;
