@@ -14,8 +14,9 @@
  * decoder_main == the 4 sequential SOT steps of Whisper.cpp:214-217, decoder_loop == one step of :219-222.
  *
  * On the B200 the KV caches never leave HBM: cross_k/v produced by b200w_encoder and the self-attention cache
- * stay resident in the engine (bf16, head-major), so the decoder calls take only (tokens, offset); the mask of the
- * reference graph is implied by offset (mask[j] = j >= offset, export_onnx.py:59-68).  Every pointer is a plain
+ * stay resident in the engine (bf16, head-major), so decoder_main / decoder_loop take only (tokens, offset); the mask of the
+ * reference graph is implied by offset (mask[j] = j >= offset, export_onnx.py:59-68).  The reference's stateless form --
+ * every cache an input, new rows an output -- is b200w_decoder_step together with b200w_{set,get}_{cross,self}_kv below.  Every pointer is a plain
  * HOST pointer unless its name ends in _dev; every function returns 0 on success and -1 on error
  * (message via b200w_last_error()).  No function falls back to the CPU.
  */
@@ -69,6 +70,30 @@ B200W_API int b200w_decoder_main(b200w_engine* e, const int* sot_tokens, int n_t
 B200W_API int b200w_decoder_loop(b200w_engine* e, const int* tokens, int offset, int B, float* logits, float* this_self_k,
                                  float* this_self_v);
 
+/* ---- the caches as tensors (the reference graph's in1..in4 / out1..out2) ------------------------------------------------
+ * The reference's decoder is stateless: self_k/v [L][B][448][d], cross_k/v [L][B][1500][d], offset and mask[448] go IN at every
+ * step and this_self_k/v [L][B][d] come OUT (export_onnx.py:668-670; AxModelRunner::set_input / get_output,
+ * ax_model_runner.cpp:110-171; call site Whisper.cpp:306-326, cache row update :328-342).  Here the caches stay resident, and
+ * these entry points move them across the boundary in the reference's f32 token-major layouts, so a caller can supply an
+ * encoder output of its own, fork or resume a decode, or read the updated cache back. */
+/* resident cross K/V of sequences [b0, b0 + nb) -> cross_k / cross_v [L][nb][1500][d] f32 (either may be NULL) */
+B200W_API int b200w_get_cross_kv(b200w_engine* e, int b0, int nb, float* cross_k, float* cross_v);
+/* cross_k / cross_v [L][B][1500][d] f32 -> resident cache (replaces b200w_encoder's result for sequences 0..B-1) */
+B200W_API int b200w_set_cross_kv(b200w_engine* e, const float* cross_k, const float* cross_v, int B);
+/* self_k / self_v [L][B][448][d] f32, rows [0, n_valid) of every sequence -> resident self-attention cache */
+B200W_API int b200w_set_self_kv(b200w_engine* e, const float* self_k, const float* self_v, int n_valid, int B);
+/* resident self-attention cache rows [0, n_rows) -> self_k / self_v [L][B][n_rows][d] f32 */
+B200W_API int b200w_get_self_kv(b200w_engine* e, float* self_k, float* self_v, int n_rows, int B);
+/* One decoder run with the reference graph's full input list.  Any of self_k/self_v/cross_k/cross_v may be NULL = keep the
+ * resident tensor; mask (may be NULL) must be the causal mask the reference host builds, mask[j] = (j >= offset)
+ * (Whisper.cpp:201,:253-258), anything else is rejected.  logits [B][n_vocab], this_self_k/v [L][B][d] (row `offset`). */
+B200W_API int b200w_decoder_step(b200w_engine* e, const int* tokens, const float* self_k, const float* self_v, const float* cross_k,
+                                 const float* cross_v, int offset, const int* mask, int B, float* logits, float* this_self_k,
+                                 float* this_self_v);
+/* With logits_out in b200w_greedy: copy only these sequences' logits, logits_out becomes [max_new_tokens][n][n_vocab]
+ * (n = 0 restores "all sequences"). */
+B200W_API int b200w_set_logit_rows(b200w_engine* e, const int* rows, int n);
+
 /* Greedy loop of Whisper::run (Whisper.cpp:200-222) on the resident cross K/V of the last b200w_encoder call.
  * forced_tokens [B][forced_len] (or NULL): teacher forcing.  logits_out [max_new_tokens][B][n_vocab] or NULL.
  * tokens_out [B][max_tokens], n_tokens_out [B]. */
@@ -99,6 +124,9 @@ B200W_API int b200w_mel_tables(int n_mels, float* bank /*[n_mels][201]*/, float*
 B200W_API int b200w_test_parse_config(const char* model_path, const char* model_type, b200w_dims* out, int* n_languages);
 B200W_API int b200w_test_load_wav(const char* path, float* out, int capacity_frames, int* n_frames, int* n_channels, int* sample_rate);
 B200W_API int b200w_test_base64(const char* in, unsigned char* out, int capacity);
+/* token table loader + detokeniser of the outer API (Whisper.cpp:115-127, :224-229) on a {type}-tokens.txt file: the bytes of
+ * ids[0..n) concatenated into out (may contain NUL); returns the full length, -1 on error. */
+B200W_API int b200w_test_detokenize(const char* tokens_file, const int* ids, int n, unsigned char* out, int capacity);
 
 #ifdef __cplusplus
 }

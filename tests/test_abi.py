@@ -126,3 +126,89 @@ def test_tokens_file_format(tmp_path):
     assert len(lines) == 300
     tok, rank = lines[42].split(" ")
     assert rank == "42" and base64.b64decode(tok) == b" t42"  # "<base64> <rank>", line index = id (export_onnx.py:415-417)
+
+
+def _write_aiff(path, data, sr=16000, bits=16, aifc=False):
+    """FORM/AIFF (big-endian PCM) or FORM/AIFC with 32-bit floats; the sample rate is an 80-bit extended float."""
+    n_frames, n_ch = data.shape
+    if aifc:
+        raw = data.astype(">f4").tobytes()
+        bits = 32
+    elif bits == 16:
+        raw = (data * 32768).clip(-32768, 32767).astype(">i2").tobytes()
+    elif bits == 8:
+        raw = (data * 128).clip(-128, 127).astype("i1").tobytes()
+    elif bits == 24:
+        v = (data.astype(np.float64) * 8388608).clip(-8388608, 8388607).astype(np.int32).reshape(-1)
+        raw = b"".join(int(x).to_bytes(3, "big", signed=True) for x in v)
+    else:
+        raw = (data.astype(np.float64) * 2147483647).clip(-2147483647, 2147483647).astype(">i4").tobytes()
+    exp = 16383 + sr.bit_length() - 1
+    ext = struct.pack(">HQ", exp, sr << (64 - sr.bit_length()))
+    comm = struct.pack(">hIh", n_ch, n_frames, bits) + ext + ((b"fl32" + b"\x00\x00") if aifc else b"")
+    ssnd = struct.pack(">II", 0, 0) + raw
+    chunks = (b"FVER" + struct.pack(">II", 4, 0xA2805140) if aifc else b"") + b"COMM" + struct.pack(">I", len(comm)) + comm + \
+        b"ANNO" + struct.pack(">I", 3) + b"abc\x00" + b"SSND" + struct.pack(">I", len(ssnd)) + ssnd
+    open(path, "wb").write(b"FORM" + struct.pack(">I", 4 + len(chunks)) + (b"AIFC" if aifc else b"AIFF") + chunks)
+
+
+@pytest.mark.parametrize("bits,aifc,tol", [(16, False, 1 / 32768), (8, False, 1 / 128), (24, False, 1 / 8388608), (32, False, 1e-6), (32, True, 0)])
+def test_aiff_reader(pkg, tmp_path, bits, aifc, tol):
+    """RunFile accepts what AudioFile<float>::load accepts: AIFF / AIFC next to WAV (AudioFile.h:490, :643-770)."""
+    lib = pkg.load_library()
+    data = np.random.default_rng(1).uniform(-0.9, 0.9, (777, 2)).astype(np.float32)
+    p = str(tmp_path / "t.aiff")
+    _write_aiff(p, data, bits=bits, aifc=aifc)
+    out = np.zeros((777, 2), np.float32)
+    nf, nc, sr = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    assert lib.b200w_test_load_wav(p.encode(), out.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), 777, ctypes.byref(nf), ctypes.byref(nc), ctypes.byref(sr)) == 0, lib.b200w_last_error()
+    assert (nf.value, nc.value, sr.value) == (777, 2, 16000)
+    assert np.abs(out - data).max() <= tol + 1e-7
+    open(p, "wb").write(b"FORM\x00\x00\x00\x04AIFF")  # no COMM / SSND
+    assert lib.b200w_test_load_wav(p.encode(), None, 0, ctypes.byref(nf), ctypes.byref(nc), ctypes.byref(sr)) == -1
+
+
+def _detok(lib, path, ids):
+    ids = np.ascontiguousarray(ids, np.int32)
+    buf = ctypes.create_string_buffer(1 << 16)
+    n = lib.b200w_test_detokenize(path.encode(), ids.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), len(ids), buf, len(buf))
+    assert n >= 0, lib.b200w_last_error()
+    return buf.raw[:n]
+
+
+def test_detokenise_real_tiktoken_vocabulary(pkg, tmp_path):
+    """{type}-tokens.txt generated from the reference's own BPE asset (export_onnx.py:391-417 does the same), then every id
+    through the library's token-table loader + detokeniser (Whisper.cpp:115-127, :224-229).  The 33-byte token 38538 and the
+    NUL token 188 overflow / truncate in the reference's char[32] + strlen path; here they round-trip."""
+    asset = "/root/reference/python/assets/multilingual.tiktoken"
+    if not os.path.exists(asset):
+        pytest.skip("reference tree not present (the GPU box): the committed edge-case fixture is used by test_detokenise_edge_case_fixture")
+    lib = pkg.load_library()
+    p = str(tmp_path / "real-tokens.txt")
+    make_model.write_tokens(p, tiktoken_path=asset)
+    table = [base64.b64decode(l.split()[0]) for l in open(asset) if l.strip()]
+    assert len(table) == 50257 and len(open(p).read().splitlines()) == 50257
+    assert table[188] == b"\x00" and len(table[38538]) == 33
+    for lo in range(0, 50257, 4096):  # every id, in runs (the hook concatenates)
+        ids = list(range(lo, min(lo + 4096, 50257)))
+        assert _detok(lib, p, ids) == b"".join(table[i] for i in ids)
+    seq = [38538, 188, 38538, 50257, 50363, 51864, 220, 188]  # specials (>= 50257) carry no text and are skipped
+    assert _detok(lib, p, seq) == table[38538] + b"\x00" + table[38538] + table[220] + b"\x00"
+    assert _detok(lib, p, [-1, 10 ** 6]) == b""
+
+
+def test_detokenise_edge_case_fixture(pkg, tmp_path):
+    """Same check from the committed fixture (tests/golden/tiktoken_edge_cases.json, written by tools/make_golden.py from the
+    reference's multilingual.tiktoken): the longest tokens, the NUL token, multi-byte UTF-8 fragments."""
+    import json
+    fx = json.load(open(os.path.join(util.ROOT, "tests", "golden", "tiktoken_edge_cases.json")))
+    lib = pkg.load_library()
+    ids = sorted(int(k) for k in fx["tokens"])
+    n = max(ids) + 1
+    p = str(tmp_path / "edge-tokens.txt")
+    with open(p, "w") as f:
+        for i in range(n):
+            f.write("%s %d\n" % (fx["tokens"].get(str(i), base64.b64encode((" t%d" % i).encode()).decode()), i))
+    want = b"".join(base64.b64decode(fx["tokens"][str(i)]) for i in ids)
+    assert _detok(lib, p, ids) == want
+    assert any(len(base64.b64decode(v)) == 33 for v in fx["tokens"].values()) and any(b"\x00" in base64.b64decode(v) for v in fx["tokens"].values())

@@ -93,3 +93,61 @@ def test_eot_is_honoured(setup):
     eot = int(oracle.cfg["eot"])
     assert all(eot not in t for t in toks)
     assert util.tokens_agree(toks, ref["tokens"], ref["top2_margin"], 2 * util.logit_tol(np.stack(ref["logits"])))
+
+
+def test_stateless_decoder_step(setup, pkg):
+    """The reference decoder's own contract (export_onnx.py:668-670, Whisper.cpp:306-326): tokens, self_k/v, cross_k/v,
+    offset and mask go IN, logits and this_self_k/v come OUT.  Every cache is the ORACLE's here, so the step is compared
+    with the encoder and the previous steps taken out; the updated cache is read back through the same boundary."""
+    eng, oracle, ck, cv, B = setup
+    L, d = oracle.l_dec, oracle.d
+    sot = oracle.sot_sequence("zh")
+    self_k = torch.zeros(L, B, 448, d)
+    self_v = torch.zeros(L, B, 448, d)
+    mask = torch.ones(448, dtype=torch.int32)
+    toks = [torch.full((B,), t) for t in sot] + [torch.tensor([100 + b for b in range(B)]), torch.tensor([2000 + 7 * b for b in range(B)])]
+    with torch.no_grad():
+        for i, t in enumerate(toks[:-1]):
+            if i > 0:
+                mask[i - 1] = 0
+            _, rk, rv = oracle.decoder_step(t, self_k, self_v, ck, cv, i, mask)
+            self_k[:, :, i], self_v[:, :, i] = rk, rv
+        off = len(toks) - 1
+        mask[off - 1] = 0
+        rl, rk, rv = oracle.decoder_step(toks[-1], self_k, self_v, ck, cv, off, mask)
+    logits, k1, v1 = eng.decoder_step(toks[-1].numpy(), off, self_k=self_k.numpy(), self_v=self_v.numpy(), cross_k=ck.numpy(),
+                                      cross_v=cv.numpy(), mask=mask.numpy())
+    err = np.abs(logits - rl.numpy()).max()
+    print("stateless step: logits max-abs err %.4f (tol %.4f)" % (err, util.logit_tol(rl.numpy())))
+    assert err <= util.logit_tol(rl.numpy())
+    assert np.abs(k1 - rk.numpy()).max() <= 2e-2 * max(1.0, float(rk.abs().max()))
+    assert np.abs(v1 - rv.numpy()).max() <= 2e-2 * max(1.0, float(rv.abs().max()))
+    # the cache that went in comes back (bf16-rounded) with the new row appended at `off`
+    sk, sv = eng.get_self_kv(B, off + 1)
+    assert np.abs(sk[:, :, :off] - self_k[:, :, :off].numpy()).max() <= 2 ** -8 * float(self_k.abs().max())
+    assert np.abs(sk[:, :, off] - k1).max() <= 2 ** -7 * max(1.0, float(np.abs(k1).max()))
+    assert np.abs(sv[:, :, off] - v1).max() <= 2 ** -7 * max(1.0, float(np.abs(v1).max()))
+    # keeping the resident caches (NULL inputs) and stepping again == the stateful decoder_loop
+    nxt = np.array([31 + b for b in range(B)], np.int32)
+    l_a, _, _ = eng.decoder_step(nxt, off + 1)
+    l_b, _, _ = eng.decoder_loop(nxt, off + 1)
+    assert np.array_equal(l_a, l_b)
+    # a mask that is not the causal one of Whisper.cpp:253-258 is refused, not silently ignored
+    bad = mask.numpy().copy()
+    bad[0] = 1
+    with pytest.raises(pkg.B200Error):
+        eng.decoder_step(nxt, off + 1, mask=bad)
+
+
+def test_batch_beyond_capacity_is_an_error(setup, pkg):
+    """greedy / decoder_main / decoder_loop on more sequences than the resident workspace holds must fail
+    cleanly instead of writing out of bounds."""
+    eng, oracle, ck, cv, B = setup
+    with pytest.raises(pkg.B200Error):
+        eng.greedy(B + 7, max_new_tokens=2, honor_eot=False)
+    with pytest.raises(pkg.B200Error):
+        eng.decoder_loop(np.zeros(B + 7, np.int32), 4)
+    with pytest.raises(pkg.B200Error):
+        eng.decoder_main(eng.sot_sequence("zh"), B + 7)
+    toks, _ = eng.greedy(B, max_new_tokens=2, honor_eot=False)  # the engine is still usable
+    assert len(toks) == B

@@ -9,7 +9,7 @@ import mel_oracle
 import util
 
 
-@pytest.mark.parametrize("arch", ["micro"])
+@pytest.mark.parametrize("arch", ["micro", "tiny"])
 def test_oracle_reproduces_golden(arch):
     torch.set_num_threads(8)
     g = np.load(os.path.join(util.ROOT, "tests", "golden", "oracle_%s.npz" % arch))

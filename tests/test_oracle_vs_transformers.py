@@ -62,8 +62,10 @@ def _hf_model(arch, W):
     return m
 
 
-@pytest.mark.parametrize("arch", ["micro"])
-def test_oracle_matches_transformers(arch):
+# micro: the CPU-test architecture; tiny: a Whisper release (d = 384); small: the headline architecture (d = 768, 12 + 12 layers),
+# one chunk.  fp32 on CPU both sides: agreement <= 2e-4 on every architecture (measured ~2e-6 on the encoder output).
+@pytest.mark.parametrize("arch,n_chunks,tol", [("micro", 2, 2e-4), ("tiny", 2, 2e-4), ("small", 1, 2e-4)])
+def test_oracle_matches_transformers(arch, n_chunks, tol):
     torch.set_num_threads(8)
     W = make_model.init_weights(arch)
     cfg = make_model.make_config(arch)
@@ -71,17 +73,20 @@ def test_oracle_matches_transformers(arch):
     o = whisper_oracle.Oracle(W, cfg)
     hf = _hf_model(arch, W)
     rng = np.random.default_rng(3)
-    mel = (rng.random((2, cfg["n_mels"], 3000), dtype=np.float32) * 2 - 1)
+    mel = (rng.random((n_chunks, cfg["n_mels"], 3000), dtype=np.float32) * 2 - 1)
     with torch.no_grad():
         xa = o.audio_features(mel)
         hf_xa = hf.model.encoder(torch.from_numpy(mel)).last_hidden_state
-        assert float((xa - hf_xa).abs().max()) <= 2e-4
+        enc_err = float((xa - hf_xa).abs().max())
+        print("%s encoder output: max-abs diff vs transformers %.2e (max |x| %.2f)" % (arch, enc_err, float(xa.abs().max())))
+        assert enc_err <= tol
         ck, cv = o.encoder(mel)
         r = o.greedy(ck, cv, max_new_tokens=6, honor_eot=False, keep_logits=True)
         # full-sequence causal decoding in transformers == our step-by-step decoding with the static cache
-        ids = torch.tensor([o.sot_sequence("zh") + r["tokens"][b][:5] for b in range(2)])
+        ids = torch.tensor([o.sot_sequence("zh") + r["tokens"][b][:5] for b in range(n_chunks)])
         hf_logits = hf(input_features=torch.from_numpy(mel), decoder_input_ids=ids).logits
     ours = np.stack(r["logits"])  # [6, B, V]: logits after consuming positions 3..8
     for i in range(6):
         diff = np.abs(hf_logits[:, 3 + i].numpy() - ours[i]).max()
-        assert diff <= 2e-4, "step %d: %g" % (i, diff)
+        assert diff <= tol, "step %d: %g" % (i, diff)
+    print("%s logits: %d steps within %.0e of transformers" % (arch, 6, tol))

@@ -98,16 +98,36 @@ def logit_tol(ref_logits):
     return LOGIT_REL_TOL * float(np.abs(ref_logits).max())
 
 
-def tokens_agree(got, exp, margins, tol):
-    """Greedy sequences must be identical up to the first step whose reference top-2 margin is below `tol`
-    (after such a step the free-running sequences may legitimately diverge)."""
+def token_report(got, exp, margins, tol):
+    """Per sequence: how many positions were compared before the first divergence, where it diverged and the oracle's
+    top-2 margin there.  A sequence is ok when it is identical to the oracle's (same length), or when its first divergence
+    sits on a step whose reference top-2 margin is below `tol` (after such a step free-running sequences may legitimately
+    differ; a shorter or longer output without such a step is a failure)."""
+    rep = []
     for b in range(len(exp)):
-        for i in range(min(len(got[b]), len(exp[b]))):
-            if got[b][i] != exp[b][i]:
-                if margins[i][b] >= tol:
-                    return False
-                break
-    return True
+        n = min(len(got[b]), len(exp[b]))
+        div = next((i for i in range(n) if got[b][i] != exp[b][i]), None)
+        if div is None and len(got[b]) != len(exp[b]):
+            div = n  # one side stopped early: a divergence at the first missing position
+        margin = float(margins[div][b]) if div is not None and div < len(margins) else None
+        ok = div is None or (margin is not None and margin < tol)
+        rep.append(dict(seq=b, len_got=len(got[b]), len_ref=len(exp[b]), compared=n if div is None else div, first_divergence=div,
+                        margin_at_divergence=margin, ok=bool(ok)))
+    return rep
+
+
+def tokens_agree(got, exp, margins, tol, min_compared=1, verbose=True):
+    """Greedy sequences must be identical up to the first step whose reference top-2 margin is below `tol`.  Prints what was
+    actually compared; fails when a sequence diverges at a confident step, when lengths differ without such a step, or when
+    fewer than `min_compared` positions were compared in total (a vacuous pass)."""
+    assert len(got) == len(exp), "sequence count differs: %d vs %d" % (len(got), len(exp))
+    rep = token_report(got, exp, margins, tol)
+    total = sum(r["compared"] for r in rep)
+    if verbose:
+        for r in rep:
+            print("  tokens seq %(seq)d: compared %(compared)d of %(len_ref)d, first divergence %(first_divergence)s, margin there %(margin_at_divergence)s, ok %(ok)s" % r)
+        print("  tokens: %d positions compared in total (tol %.4f)" % (total, tol))
+    return all(r["ok"] for r in rep) and total >= min_compared
 
 
 def cosine(a, b):

@@ -4,6 +4,7 @@
   mel_golden.npz      outputs of the reference's OWN C++ frontend (oracle/_ref/libmel_ref.so, compiled from
                       /root/reference/cpp/src) on seeded synthetic audio: one demo.wav-shaped clip in full and
                       strided samples of 30 s chunks for the N / U / S distributions at 80 and 128 mel bins.
+  tiktoken_edge_cases.json  the awkward entries of the reference's BPE asset (NUL token, 25..33-byte tokens, UTF-8 fragments)
   oracle_micro.npz    outputs of the torch-CPU restatement (oracle/whisper_oracle.py) for the `micro` and
   oracle_tiny.npz     `tiny` architectures on a seeded mel input: strided cross K/V, per-step top-8 logits,
                       top-2 margins and greedy tokens.  The reference has no runnable encoder/decoder here
@@ -50,6 +51,19 @@ def main():
                             cross_k=ck.numpy()[:, :, ::50, ::4].astype(np.float16), cross_v=cv.numpy()[:, :, ::50, ::4].astype(np.float16),
                             tokens=np.array(r["tokens"], np.int32), margins=np.stack(r["top2_margin"]).astype(np.float32),
                             top_idx=top_idx, top_val=top_val)
+    # edge cases of the reference's BPE vocabulary (python/assets/multilingual.tiktoken; /root/reference is absent on the GPU
+    # box): the NUL token, every token longer than 24 bytes (the reference detokenises into char[32]), a few UTF-8 fragments
+    import base64
+    import json
+    asset = "/root/reference/python/assets/multilingual.tiktoken"
+    rows = [l.split() for l in open(asset) if l.strip()]
+    pick = {}
+    for tok, rank in rows:
+        raw = base64.b64decode(tok)
+        if b"\x00" in raw or len(raw) > 24 or int(rank) in (220, 11, 13, 50256) or (len(pick) < 400 and raw[:1] >= b"\xe0" and int(rank) % 37 == 0):
+            pick[rank] = tok
+    json.dump({"source": "multilingual.tiktoken of the reference (python/assets), ids -> base64 token bytes", "tokens": pick},
+              open(os.path.join(OUT, "tiktoken_edge_cases.json"), "w"), indent=0)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -219,7 +219,9 @@ def build_model_dir(root, arch, seed=None, tiktoken_path=None, weights=None):
     d = os.path.join(root, arch)
     os.makedirs(d, exist_ok=True)
     W = weights if weights is not None else init_weights(arch, seed)
-    dims = dims_from_weights(W) if (weights is not None and arch not in ARCHS) else None
+    # a checkpoint's configuration always comes from its own tensor shapes: `--name turbo` on a large-v3 checkpoint must not
+    # silently write the 4-layer turbo table next to 32 decoder layers of weights
+    dims = dims_from_weights(W) if weights is not None else None
     enc = {k: v for k, v in W.items() if is_encoder_file_tensor(k)}
     dec = {k: v for k, v in W.items() if not is_encoder_file_tensor(k)}
     write_b200w(os.path.join(d, "%s-encoder.b200w" % arch), enc)

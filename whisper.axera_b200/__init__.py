@@ -51,7 +51,8 @@ EXPORTED_SYMBOLS = [
     "b200w_last_error", "b200w_engine_create", "b200w_engine_destroy", "b200w_get_dims", "b200w_sot_sequence",
     "b200w_logmel", "b200w_encoder", "b200w_decoder_main", "b200w_decoder_loop", "b200w_greedy", "b200w_transcribe",
     "b200w_upload_pcm", "b200w_transcribe_resident", "b200w_time_stage", "b200w_selftest_gemm", "b200w_mel_tables",
-    "b200w_test_parse_config", "b200w_test_load_wav", "b200w_test_base64", "b200w_selftest_attention", "b200w_selftest_cross_attention",
+    "b200w_get_cross_kv", "b200w_set_cross_kv", "b200w_set_self_kv", "b200w_get_self_kv", "b200w_decoder_step", "b200w_set_logit_rows",
+    "b200w_test_parse_config", "b200w_test_load_wav", "b200w_test_base64", "b200w_test_detokenize", "b200w_selftest_attention", "b200w_selftest_cross_attention",
 ]
 
 _lib = None
@@ -88,6 +89,12 @@ def load_library():
     lib.b200w_encoder.argtypes = [vp, _c_float_p, ci, _c_float_p, _c_float_p]
     lib.b200w_decoder_main.argtypes = [vp, _c_int_p, ci, ci, _c_float_p, _c_float_p, _c_float_p]
     lib.b200w_decoder_loop.argtypes = [vp, _c_int_p, ci, ci, _c_float_p, _c_float_p, _c_float_p]
+    lib.b200w_get_cross_kv.argtypes = [vp, ci, ci, _c_float_p, _c_float_p]
+    lib.b200w_set_cross_kv.argtypes = [vp, _c_float_p, _c_float_p, ci]
+    lib.b200w_set_self_kv.argtypes = [vp, _c_float_p, _c_float_p, ci, ci]
+    lib.b200w_get_self_kv.argtypes = [vp, _c_float_p, _c_float_p, ci, ci]
+    lib.b200w_decoder_step.argtypes = [vp, _c_int_p, _c_float_p, _c_float_p, _c_float_p, _c_float_p, ci, _c_int_p, ci, _c_float_p, _c_float_p, _c_float_p]
+    lib.b200w_set_logit_rows.argtypes = [vp, _c_int_p, ci]
     lib.b200w_greedy.argtypes = [vp, ci, cp, ci, ci, _c_int_p, ci, _c_float_p, _c_int_p, ci, _c_int_p]
     lib.b200w_transcribe.argtypes = [vp, _c_float_p, cl, _c_int_p, ci, cp, ci, ci, _c_int_p, ci, _c_int_p, ctypes.POINTER(Times)]
     lib.b200w_upload_pcm.argtypes = [vp, _c_float_p, cl, _c_int_p, ci]
@@ -100,6 +107,7 @@ def load_library():
     lib.b200w_test_parse_config.argtypes = [cp, cp, ctypes.POINTER(Dims), _c_int_p]
     lib.b200w_test_load_wav.argtypes = [cp, _c_float_p, ci, _c_int_p, _c_int_p, _c_int_p]
     lib.b200w_test_base64.argtypes = [cp, ctypes.c_char_p, ci]
+    lib.b200w_test_detokenize.argtypes = [cp, _c_int_p, ci, ctypes.c_char_p, ci]
     _lib = lib
     return lib
 
@@ -200,14 +208,59 @@ class Engine:
         self._check(self.lib.b200w_decoder_loop(self.h, _ip(toks), int(offset), B, _fp(logits), _fp(k), _fp(v)))
         return logits, k, v
 
-    def greedy(self, batch, language="zh", max_new_tokens=0, honor_eot=True, forced_tokens=None, keep_logits=False):
+    def get_cross_kv(self, b0, nb):
+        """resident cross K/V of sequences [b0, b0 + nb) as f32 [L, nb, 1500, d] (the reference encoder's out0 / out1)."""
+        L, d = self.dims.n_text_layer, self.dims.d_model
+        ck = np.empty((L, nb, N_AUDIO_CTX, d), np.float32)
+        cv = np.empty((L, nb, N_AUDIO_CTX, d), np.float32)
+        self._check(self.lib.b200w_get_cross_kv(self.h, b0, nb, _fp(ck), _fp(cv)))
+        return ck, cv
+
+    def set_cross_kv(self, cross_k, cross_v):
+        ck = np.ascontiguousarray(cross_k, np.float32)
+        cv = np.ascontiguousarray(cross_v, np.float32)
+        assert ck.shape == cv.shape and ck.shape[0] == self.dims.n_text_layer and ck.shape[2:] == (N_AUDIO_CTX, self.dims.d_model)
+        self._check(self.lib.b200w_set_cross_kv(self.h, _fp(ck), _fp(cv), ck.shape[1]))
+
+    def set_self_kv(self, self_k, self_v, n_valid):
+        sk = np.ascontiguousarray(self_k, np.float32)
+        sv = np.ascontiguousarray(self_v, np.float32)
+        assert sk.shape == sv.shape and sk.shape[2:] == (N_TEXT_CTX, self.dims.d_model)
+        self._check(self.lib.b200w_set_self_kv(self.h, _fp(sk), _fp(sv), int(n_valid), sk.shape[1]))
+
+    def get_self_kv(self, batch, n_rows):
+        L, d = self.dims.n_text_layer, self.dims.d_model
+        sk = np.empty((L, batch, n_rows, d), np.float32)
+        sv = np.empty((L, batch, n_rows, d), np.float32)
+        self._check(self.lib.b200w_get_self_kv(self.h, _fp(sk), _fp(sv), n_rows, batch))
+        return sk, sv
+
+    def decoder_step(self, tokens, offset, self_k=None, self_v=None, cross_k=None, cross_v=None, mask=None):
+        """The reference decoder graph's stateless call: every cache may be passed in (None = keep the resident one)."""
+        L, d, V = self.dims.n_text_layer, self.dims.d_model, self.dims.n_vocab
+        toks = np.ascontiguousarray(tokens, np.int32)
+        B = len(toks)
+        f = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
+        sk, sv, ck, cv = f(self_k), f(self_v), f(cross_k), f(cross_v)
+        m = None if mask is None else np.ascontiguousarray(mask, np.int32)
+        logits = np.empty((B, V), np.float32)
+        k = np.empty((L, B, d), np.float32)
+        v = np.empty((L, B, d), np.float32)
+        self._check(self.lib.b200w_decoder_step(self.h, _ip(toks), _fp(sk), _fp(sv), _fp(ck), _fp(cv), int(offset), _ip(m), B, _fp(logits),
+                                                _fp(k), _fp(v)))
+        return logits, k, v
+
+    def greedy(self, batch, language="zh", max_new_tokens=0, honor_eot=True, forced_tokens=None, keep_logits=False, logit_rows=None):
+        """logit_rows: with keep_logits, only these sequences' logits are returned ([n_steps, len(logit_rows), V])."""
         forced = None
         flen = 0
         if forced_tokens is not None:
             forced = np.ascontiguousarray(forced_tokens, np.int32)
             flen = forced.shape[1]
         n_max = max_new_tokens if max_new_tokens > 0 else N_TEXT_CTX - 4
-        logits = np.zeros((n_max, batch, self.dims.n_vocab), np.float32) if keep_logits else None
+        rows = np.ascontiguousarray(logit_rows if logit_rows is not None else [], np.int32)
+        self._check(self.lib.b200w_set_logit_rows(self.h, _ip(rows), len(rows)))
+        logits = np.zeros((n_max, len(rows) if len(rows) else batch, self.dims.n_vocab), np.float32) if keep_logits else None
         toks = np.zeros((batch, N_TEXT_CTX), np.int32)
         n = np.zeros(batch, np.int32)
         self._check(self.lib.b200w_greedy(self.h, batch, language.encode(), max_new_tokens, int(honor_eot), _ip(forced), flen,

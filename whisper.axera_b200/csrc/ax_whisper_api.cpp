@@ -36,6 +36,7 @@ struct PendingRequest {
   std::vector<int> tokens;
   int rc = 0;
   std::string err;
+  bool filled = false;  // rc / tokens / err are final
   bool done = false;
 };
 
@@ -43,7 +44,7 @@ struct WhisperHandle {
   std::unique_ptr<Engine> engine;                // device 0 of the handle (config, SOT sequence)
   std::vector<std::unique_ptr<Engine>> extra;    // further devices (B200W_DEVICES): own weights, contexts, streams
   std::vector<std::unique_ptr<std::mutex>> extra_mu;
-  std::vector<std::string> token_table;  // base64 text per id (line index = id, Whisper.cpp:123-126)
+  TokenTable token_table;                // base64 text per id (line index = id, Whisper.cpp:123-126)
   std::string lang;
   std::mutex mu;                         // the engine (one GPU pass at a time)
   // request coalescing: calls that arrive while a pass is running are transcribed together in the next pass
@@ -62,14 +63,9 @@ void set_err(const std::string& s) {
 }
 
 std::string detokenize(const WhisperHandle& h, const std::vector<int>& ids) {
-  std::string s;
-  for (int id : ids) {
-    if (id < 0 || (size_t)id >= h.token_table.size()) continue;  // specials (>= 50257) carry no text; the reference indexes OOB here
-    s += base64_decode(h.token_table[id]);
-  }
   // The reference converts Traditional -> Simplified Chinese with OpenCC when lang == "zh" (Whisper.cpp:231-236); its
   // prebuilt OpenCC is AArch64-only and the conversion is text cosmetics, not arithmetic: identity here.
-  return s;
+  return h.token_table.detokenize(ids.data(), ids.size());
 }
 
 int run_on(Engine* eng, std::mutex* mu, const std::string& lang, const float* const* pcm, const int* n_samples, int B,
@@ -101,26 +97,42 @@ int run_batch(WhisperHandle* h, const float* const* pcm, const int* n_samples, i
   }
   std::vector<std::vector<std::vector<int>>> part(G);
   std::vector<std::string> errs(G);
-  std::vector<int> rcs(G, 0);
-  std::vector<std::thread> workers;
+  std::vector<int> rcs(G, -1);
   auto shard = [&](int g) { return (int)((long)B * g / G); };
-  for (int g = 0; g < G; ++g) {
-    workers.emplace_back([&, g] {
-      Engine* eng = g == 0 ? h->engine.get() : h->extra[g - 1].get();
-      std::mutex* mu = g == 0 ? &h->mu : h->extra_mu[g - 1].get();
-      const int b0 = shard(g), b1 = shard(g + 1);
-      rcs[g] = run_on(eng, mu, h->lang, pcm + b0, n_samples + b0, b1 - b0, opt, &part[g], &errs[g]);
-    });
+  {
+    // joins whatever was started, also when a later std::thread constructor throws (a joinable thread that is destroyed
+    // would call std::terminate)
+    struct Joiner {
+      std::vector<std::thread> t;
+      ~Joiner() {
+        for (auto& w : t)
+          if (w.joinable()) w.join();
+      }
+    } workers;
+    workers.t.reserve(G);
+    try {
+      for (int g = 0; g < G; ++g) {
+        workers.t.emplace_back([&, g] {
+          Engine* eng = g == 0 ? h->engine.get() : h->extra[g - 1].get();
+          std::mutex* mu = g == 0 ? &h->mu : h->extra_mu[g - 1].get();
+          const int b0 = shard(g), b1 = shard(g + 1);
+          rcs[g] = run_on(eng, mu, h->lang, pcm + b0, n_samples + b0, b1 - b0, opt, &part[g], &errs[g]);
+        });
+      }
+    } catch (const std::exception& ex) {
+      errs[0] = std::string("run whisper failed: cannot start a worker thread: ") + ex.what();
+      rcs[0] = -1;
+    }
   }
-  for (auto& w : workers) w.join();
   toks->clear();
   for (int g = 0; g < G; ++g) {
     if (rcs[g] != 0) {
-      set_err(errs[g]);
+      set_err(errs[g].empty() ? "run whisper failed: worker did not run" : errs[g]);
       return -1;
     }
-    for (auto& t : part[g]) toks->push_back(std::move(t));
   }
+  for (int g = 0; g < G; ++g)
+    for (auto& t : part[g]) toks->push_back(std::move(t));
   return 0;
 }
 
@@ -153,25 +165,37 @@ int run_coalesced(WhisperHandle* h, const float* pcm, int n_samples, std::vector
     }
     ++h->n_passes;
     lk.unlock();
-    // requests that cannot be transcribed (too short) fail alone, not the whole pass
-    std::vector<const float*> ptrs;
-    std::vector<int> lens;
-    std::vector<PendingRequest*> ok;
-    for (PendingRequest* r : batch) {
-      if (r->n_samples < 201) {
-        r->rc = -1, r->err = "run whisper failed: audio shorter than 201 samples (reflect padding needs n_fft/2 + 1)";
-      } else {
-        ptrs.push_back(r->pcm), lens.push_back(r->n_samples), ok.push_back(r);
+    // Nothing below may leave this scope without marking the batch done and handing the leadership back: a waiter that is
+    // never woken (or a stuck leader_active flag) would block every later call on this handle for ever.
+    try {
+      // requests that cannot be transcribed (too short) fail alone, not the whole pass
+      std::vector<const float*> ptrs;
+      std::vector<int> lens;
+      std::vector<PendingRequest*> ok;
+      for (PendingRequest* r : batch) {
+        if (r->n_samples < 201) {
+          r->rc = -1, r->err = "run whisper failed: audio shorter than 201 samples (reflect padding needs n_fft/2 + 1)";
+          r->filled = true;
+        } else {
+          ptrs.push_back(r->pcm), lens.push_back(r->n_samples), ok.push_back(r);
+        }
       }
-    }
-    if (!ok.empty()) {
-      std::vector<std::vector<int>> out;
-      const int rc = run_batch(h, ptrs.data(), lens.data(), (int)ok.size(), DecodeOptions(), &out);
-      for (size_t i = 0; i < ok.size(); ++i) {
-        ok[i]->rc = rc;
-        if (rc == 0) ok[i]->tokens = std::move(out[i]);
-        else ok[i]->err = g_api_err;
+      if (!ok.empty()) {
+        std::vector<std::vector<int>> out;
+        const int rc = run_batch(h, ptrs.data(), lens.data(), (int)ok.size(), DecodeOptions(), &out);
+        for (size_t i = 0; i < ok.size(); ++i) {
+          ok[i]->rc = rc;
+          if (rc == 0) ok[i]->tokens = std::move(out[i]);
+          else ok[i]->err = g_api_err;
+          ok[i]->filled = true;
+        }
       }
+    } catch (const std::exception& ex) {
+      for (PendingRequest* r : batch)
+        if (!r->filled) r->rc = -1, r->err = std::string("run whisper failed: ") + ex.what();
+    } catch (...) {
+      for (PendingRequest* r : batch)
+        if (!r->filled) r->rc = -1, r->err = "run whisper failed: unknown error";
     }
     lk.lock();
     for (PendingRequest* r : batch) r->done = true;
@@ -227,13 +251,11 @@ AX_WHISPER_API AX_WHISPER_HANDLE AX_WHISPER_Init(const char* model_type, const c
       h->extra_mu.emplace_back(new std::mutex());
     }
     const std::string token_path = std::string(model_path) + "/" + model_type + "/" + model_type + "-tokens.txt";
-    std::ifstream fs(token_path);
-    if (!fs.is_open()) {
-      set_err("Can NOT open " + token_path);
+    std::string terr;
+    if (!h->token_table.load(token_path, &terr)) {
+      set_err(terr);
       return nullptr;
     }
-    std::string line;
-    while (std::getline(fs, line)) h->token_table.push_back(line.substr(0, line.find(' ')));
     h->engine->sot_sequence(language, &h->lang);  // resolves the "unknown language -> zh" fallback once
     if (const char* e = getenv("B200W_COALESCE_MAX")) h->coalesce_max = std::max(1, atoi(e));
     if (const char* e = getenv("B200W_COALESCE_WAIT_US")) h->coalesce_wait_us = std::max(0, atoi(e));

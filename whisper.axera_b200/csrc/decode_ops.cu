@@ -531,6 +531,39 @@ __global__ void __launch_bounds__(128) argmax_finalize_kernel(DecodeState st, co
   }
 }
 
+// ---- K/V cache import / export (model-ABI boundary: the reference's decoder takes and returns f32 [B][T][d] caches) ----
+// f32 [n_seq][T_src][d] (token-major, the reference layout) <-> bf16 head-major [n_seq][H][T_dst][64] (resident layout);
+// rows [0, n_rows) of every sequence are converted.  One thread per 8 consecutive features of one (sequence, row, head).
+__global__ void kv_import_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int n_seq, int n_rows, int T_src, int T_dst, int n_head) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;  // ((seq * n_rows + t) * n_head + h) * 8 + part
+  const long total = (long)n_seq * n_rows * n_head * 8;
+  if (i >= total) return;
+  const int part = (int)(i & 7);
+  long r = i >> 3;
+  const int h = (int)(r % n_head);
+  r /= n_head;
+  const int t = (int)(r % n_rows), b = (int)(r / n_rows);
+  const float* s = src + ((long)b * T_src + t) * n_head * 64 + h * 64 + part * 8;
+  const float4 a = *reinterpret_cast<const float4*>(s), c = *reinterpret_cast<const float4*>(s + 4);
+  uint4 o;
+  o.x = pack_bf16x2(a.x, a.y), o.y = pack_bf16x2(a.z, a.w), o.z = pack_bf16x2(c.x, c.y), o.w = pack_bf16x2(c.z, c.w);
+  *reinterpret_cast<uint4*>(dst + (((long)b * n_head + h) * T_dst + t) * 64 + part * 8) = o;
+}
+__global__ void kv_export_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int n_seq, int n_rows, int T_src, int T_dst, int n_head) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long total = (long)n_seq * n_rows * n_head * 8;
+  if (i >= total) return;
+  const int part = (int)(i & 7);
+  long r = i >> 3;
+  const int h = (int)(r % n_head);
+  r /= n_head;
+  const int t = (int)(r % n_rows), b = (int)(r / n_rows);
+  const uint4 u = *reinterpret_cast<const uint4*>(src + (((long)b * n_head + h) * T_src + t) * 64 + part * 8);
+  float* o = dst + ((long)b * T_dst + t) * n_head * 64 + h * 64 + part * 8;
+  *reinterpret_cast<float4*>(o) = make_float4(bf16lo_to_f32(u.x), bf16hi_to_f32(u.x), bf16lo_to_f32(u.y), bf16hi_to_f32(u.y));
+  *reinterpret_cast<float4*>(o + 4) = make_float4(bf16lo_to_f32(u.z), bf16hi_to_f32(u.z), bf16lo_to_f32(u.w), bf16hi_to_f32(u.w));
+}
+
 __global__ void advance_step_kernel(int* step) {
   pdl_wait();
   pdl_launch_dependents();
@@ -592,6 +625,19 @@ void decode_ops_set_attributes() {}
 void launch_argmax_finalize(const DecodeState& st, const float* part_val, const int* part_idx, int n_tiles, int part_ld, int B,
                             int n_text_ctx, int eot, int honor_eot, int sot_len, cudaStream_t stream) {
   launch_pdl(argmax_finalize_kernel, dim3(B), dim3(128), 0, stream, st, part_val, part_idx, n_tiles, part_ld, n_text_ctx, eot, honor_eot, sot_len);
+}
+
+void launch_kv_import(const float* src, __nv_bfloat16* dst, int n_seq, int n_rows, int T_src, int T_dst, int n_head, cudaStream_t stream) {
+  const long total = (long)n_seq * n_rows * n_head * 8;
+  if (total <= 0) return;
+  kv_import_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(src, dst, n_seq, n_rows, T_src, T_dst, n_head);
+  CUDA_CHECK(cudaGetLastError());
+}
+void launch_kv_export(const __nv_bfloat16* src, float* dst, int n_seq, int n_rows, int T_src, int T_dst, int n_head, cudaStream_t stream) {
+  const long total = (long)n_seq * n_rows * n_head * 8;
+  if (total <= 0) return;
+  kv_export_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(src, dst, n_seq, n_rows, T_src, T_dst, n_head);
+  CUDA_CHECK(cudaGetLastError());
 }
 
 void launch_advance_step(int* step, cudaStream_t stream, bool pdl) { launch_k(pdl, advance_step_kernel, dim3(1), dim3(1), 0, stream, step); }

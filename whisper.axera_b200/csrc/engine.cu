@@ -221,6 +221,29 @@ void Engine::load_weights(const std::string& dir, const std::string& type) {
   auto check = [](const HostTensor& t, std::initializer_list<size_t> dims, const char* name) {
     if (t.dims != std::vector<size_t>(dims)) throw std::runtime_error(std::string("unexpected shape for ") + name);
   };
+  // the weight files must describe exactly the architecture of the config: no blocks beyond n_audio_layer / n_text_layer
+  // (a deeper checkpoint converted under a shallower config would otherwise load and produce garbage), every matrix of the
+  // expected shape
+  for (const WeightFile* f : {&fe, &fd})
+    for (const auto& kv : f->tensors) {
+      const std::string& n = kv.first;
+      const bool enc = n.rfind("encoder.blocks.", 0) == 0, dec = n.rfind("decoder.blocks.", 0) == 0;
+      if (enc || dec) {
+        const int idx = atoi(n.c_str() + 15);
+        if (idx >= (enc ? cfg_.l_enc : cfg_.l_dec))
+          throw std::runtime_error("weight file holds " + n + " but the config declares only " + std::to_string(enc ? cfg_.l_enc : cfg_.l_dec) +
+                                   " such blocks");
+      }
+      const size_t ud = (size_t)d;
+      const auto ends = [&](const char* suf) { const size_t l = strlen(suf); return n.size() >= l && n.compare(n.size() - l, l, suf) == 0; };
+      if (enc || dec) {
+        if (ends(".query.weight") || ends(".key.weight") || ends(".value.weight") || ends(".out.weight")) check(kv.second, {ud, ud}, n.c_str());
+        else if (ends(".mlp.0.weight")) check(kv.second, {4 * ud, ud}, n.c_str());
+        else if (ends(".mlp.2.weight")) check(kv.second, {ud, 4 * ud}, n.c_str());
+        else if (ends(".mlp.0.bias")) check(kv.second, {4 * ud}, n.c_str());
+        else if (ends(".bias") || ends("_ln.weight")) check(kv.second, {ud}, n.c_str());
+      }
+    }
   // conv weights [d][C][3] -> [d][3][C] so that a tap is a contiguous K slice
   auto conv_reorder = [&](const HostTensor& t, int C) {
     std::vector<float> out((size_t)d * 3 * C);
@@ -345,22 +368,43 @@ std::vector<int> Engine::sot_sequence(const std::string& lang, std::string* reso
 void Engine::free_workspace() {
   for (auto& kv : graphs_) cudaGraphExecDestroy(kv.second);
   graphs_.clear();
+  per_step_launches_.clear();
   for (GemmPlan* p : plans_) gemm_plan_destroy(p);
   plans_.clear();
   enc_plans_.clear();
   dec_plans_.clear();
   for (void* p : ws_owned_) cudaFree(p);
   ws_owned_.clear();
+  // the engine is EMPTY from here until ensure_capacity() has rebuilt everything: a failed re-allocation must not leave
+  // capacities that describe freed memory
+  cap_ = 0, pcm_stride_ = 0, enc_sub_ = 0, dec_rows_pad_ = 0;
+  pcm_ = mel_ = utt_max_ = x_enc_ = x_dec_ = qkv_dec_ = q_dec_ = logits_ = part_val_ = part_m_ = part_l_ = part_o_ = nullptr;
+  n_samples_ = part_idx_ = cross_work_ = step_ctr_ = nullptr;
+  mel_tm_ = conv1_out_ = h_enc_ = qkv_enc_ = attn_enc_ = mlp_enc_ = cross_k_ = cross_v_ = self_k_ = self_v_ = nullptr;
+  h_dec_ = attn_dec_ = mlp_dec_ = nullptr;
+  st_ = DecodeState{};
 }
 
 void Engine::ensure_capacity(int B, long max_samples) {
   const long stride = std::max<long>(kChunkSamples, (max_samples + 7) / 8 * 8);
   if (B <= cap_ && stride <= pcm_stride_) return;
+  if (B <= 0) throw std::runtime_error("ensure_capacity: batch must be positive");
   CUDA_CHECK(cudaSetDevice(device_));
   CUDA_CHECK(cudaStreamSynchronize(stream_));
-  free_workspace();
-  cap_ = std::max(B, cap_);
-  pcm_stride_ = std::max(stride, pcm_stride_);
+  const int new_cap = std::max(B, cap_);
+  const long new_stride = std::max(stride, pcm_stride_);
+  free_workspace();  // resets cap_ / pcm_stride_ / pointers: the engine is empty until the allocations below succeed
+  try {
+    allocate_workspace(new_cap, new_stride);
+  } catch (...) {
+    free_workspace();  // back to the empty state (capacity 0): the next, smaller request re-allocates cleanly
+    throw;
+  }
+}
+
+void Engine::allocate_workspace(int new_cap, long new_stride) {
+  cap_ = new_cap;
+  pcm_stride_ = new_stride;
   const int d = cfg_.d, H = cfg_.n_head, L = cfg_.l_dec;
   const char* sub_env = getenv("B200W_ENC_SUB_BATCH");
   enc_sub_ = std::min(cap_, sub_env ? std::max(1, atoi(sub_env)) : 128);  // measured: larger sub-batches are slightly faster
@@ -399,7 +443,6 @@ void Engine::ensure_capacity(int B, long max_samples) {
   part_l_ = dev_alloc<float>(o, np);
   part_o_ = dev_alloc<float>(o, np * 64);
   cross_work_ = dev_alloc<int>(o, (size_t)cfg_.l_dec * 4 * 2 + 2);  // item counters of the streaming cross-attention launches
-  CUDA_CHECK(cudaMemset(cross_work_, 0, sizeof(int) * ((size_t)cfg_.l_dec * 4 * 2 + 2)));
   step_ctr_ = dev_alloc<int>(o, 4);  // one step counter per micro-batch (they advance independently inside a graph)
   st_.step = step_ctr_;
   st_.tokens = dev_alloc<int>(o, (size_t)cap_ * kTextCtx);
@@ -665,6 +708,7 @@ void Engine::enqueue_decode_step(int B, bool want_logits, bool finalize, int hon
 }
 
 void Engine::run_cross_attention_only(int B) {
+  check_batch(B, "run_cross_attention_only");
   const int H = cfg_.n_head;
   const int n_split = cross_attention_pick_split(B, H);
   for (int l = 0; l < cfg_.l_dec; ++l) {
@@ -675,7 +719,15 @@ void Engine::run_cross_attention_only(int B) {
   }
 }
 
+void Engine::check_batch(int B, const char* what) const {
+  if (B <= 0 || B > cap_)
+    throw std::runtime_error(std::string(what) + ": batch " + std::to_string(B) + " exceeds the resident capacity " + std::to_string(cap_) +
+                             " (run the encoder / upload PCM for this batch first)");
+}
+
 void Engine::decode_reset(int B) {
+  check_batch(B, "decode_reset");
+  CUDA_CHECK(cudaSetDevice(device_));
   CUDA_CHECK(cudaMemsetAsync(step_ctr_, 0, 4 * sizeof(int), stream_));
   CUDA_CHECK(cudaMemsetAsync(st_.finished, 0, sizeof(int) * B, stream_));
   CUDA_CHECK(cudaMemsetAsync(st_.forced, 0xff, sizeof(int) * (size_t)B * kTextCtx, stream_));  // -1
@@ -683,6 +735,9 @@ void Engine::decode_reset(int B) {
 
 int Engine::run_decode(int B, const std::vector<int>& sot, const DecodeOptions& opt, std::vector<std::vector<int>>* tokens) {
   if ((int)sot.size() != kSotLen) throw std::runtime_error("sot sequence must have 4 tokens");
+  check_batch(B, "run_decode");
+  for (int r = 0; r < opt.n_logit_rows; ++r)
+    if (opt.logit_rows[r] < 0 || opt.logit_rows[r] >= B) throw std::runtime_error("run_decode: logit row outside the batch");
   CUDA_CHECK(cudaSetDevice(device_));
   decode_reset(B);
   // prefill token / forcing tables
@@ -749,8 +804,15 @@ int Engine::run_decode(int B, const std::vector<int>& sot, const DecodeOptions& 
       enqueue_decode_step(B, want_logits, true, opt.honor_eot ? 1 : 0);
       if (want_logits && s >= kSotLen - 1 && s - (kSotLen - 1) < max_new) {
         // logits after consuming position s = prediction of generated token (s - 3)
-        CUDA_CHECK(cudaMemcpy2DAsync(opt.logits_out + (size_t)(s - (kSotLen - 1)) * B * cfg_.n_vocab, (size_t)cfg_.n_vocab * 4, logits_,
-                                     (size_t)vocab_pad_ * 4, (size_t)cfg_.n_vocab * 4, B, cudaMemcpyDeviceToHost, stream_));
+        const size_t step_i = (size_t)(s - (kSotLen - 1));
+        if (opt.logit_rows != nullptr) {
+          for (int r = 0; r < opt.n_logit_rows; ++r)
+            CUDA_CHECK(cudaMemcpyAsync(opt.logits_out + (step_i * opt.n_logit_rows + r) * cfg_.n_vocab, logits_ + (size_t)opt.logit_rows[r] * vocab_pad_,
+                                       (size_t)cfg_.n_vocab * 4, cudaMemcpyDeviceToHost, stream_));
+        } else {
+          CUDA_CHECK(cudaMemcpy2DAsync(opt.logits_out + step_i * B * cfg_.n_vocab, (size_t)cfg_.n_vocab * 4, logits_, (size_t)vocab_pad_ * 4,
+                                       (size_t)cfg_.n_vocab * 4, B, cudaMemcpyDeviceToHost, stream_));
+        }
       }
     }
     steps_done += k;
@@ -781,6 +843,7 @@ int Engine::run_decode(int B, const std::vector<int>& sot, const DecodeOptions& 
 
 void Engine::decode_step_tokens(int B, const int* tokens_host, int offset, float* logits_host, float* this_k, float* this_v) {
   // one decoder run on the resident caches, driven like the reference's run_decoder(token, offset)
+  check_batch(B, "decode_step_tokens");
   CUDA_CHECK(cudaSetDevice(device_));
   const int d = cfg_.d, H = cfg_.n_head, L = cfg_.l_dec;
   if (offset < 0 || offset >= kTextCtx) throw std::runtime_error("decoder offset out of range");
@@ -797,48 +860,77 @@ void Engine::decode_step_tokens(int B, const int* tokens_host, int offset, float
   CUDA_CHECK(cudaStreamSynchronize(stream_));
   if (this_k || this_v) {
     // rows just appended to the bf16 caches, returned as f32 [L][B][d]
-    std::vector<uint16_t> tmp(64);
+    float* tmp = nullptr;
+    CUDA_CHECK(cudaMalloc(&tmp, (size_t)B * d * 4));
     for (int kv = 0; kv < 2; ++kv) {
       float* dst = kv == 0 ? this_k : this_v;
       if (!dst) continue;
       const __nv_bfloat16* cache = kv == 0 ? self_k_ : self_v_;
-      for (int l = 0; l < L; ++l)
-        for (int b = 0; b < B; ++b)
-          for (int h = 0; h < H; ++h) {
-            const size_t off = ((((size_t)l * cap_ + b) * H + h) * kTextCtx + offset) * 64;
-            CUDA_CHECK(cudaMemcpy(tmp.data(), cache + off, 128, cudaMemcpyDeviceToHost));
-            for (int i = 0; i < 64; ++i) {
-              uint32_t u = (uint32_t)tmp[i] << 16;
-              float f;
-              memcpy(&f, &u, 4);
-              dst[((size_t)l * B + b) * d + h * 64 + i] = f;
-            }
-          }
+      for (int l = 0; l < L; ++l) {
+        launch_kv_export(cache + (size_t)l * cap_ * H * kTextCtx * 64 + (size_t)offset * 64, tmp, B, 1, kTextCtx, 1, H, stream_);
+        CUDA_CHECK(cudaMemcpyAsync(dst + (size_t)l * B * d, tmp, (size_t)B * d * 4, cudaMemcpyDeviceToHost, stream_));
+      }
     }
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    cudaFree(tmp);
   }
 }
 
-void Engine::read_cross_kv(int B, float* cross_k, float* cross_v) const {
+// ---- K/V caches across the model-ABI boundary (the reference's decoder graph takes self_k/v and cross_k/v as INPUTS and
+// returns the new cache rows, export_onnx.py:668-670, Whisper.cpp:306-313; here they are resident, so a caller that wants to
+// supply or inspect them goes through these converters: f32 token-major <-> bf16 head-major) ----
+void Engine::export_cache(const __nv_bfloat16* cache, int T, int b0, int nb, int n_rows, float* out) const {
+  // out [L][nb][n_rows][d] f32
   const int d = cfg_.d, H = cfg_.n_head, L = cfg_.l_dec;
-  const size_t per = (size_t)kAudioCtx * 64;
-  std::vector<uint16_t> tmp(per);
-  for (int kv = 0; kv < 2; ++kv) {
-    float* dst = kv == 0 ? cross_k : cross_v;
-    if (!dst) continue;
-    const __nv_bfloat16* src = kv == 0 ? cross_k_ : cross_v_;
-    for (int l = 0; l < L; ++l)
-      for (int b = 0; b < B; ++b)
-        for (int h = 0; h < H; ++h) {
-          CUDA_CHECK(cudaMemcpy(tmp.data(), src + (((size_t)l * cap_ + b) * H + h) * per, per * 2, cudaMemcpyDeviceToHost));
-          for (int t = 0; t < kAudioCtx; ++t)
-            for (int i = 0; i < 64; ++i) {
-              uint32_t u = (uint32_t)tmp[(size_t)t * 64 + i] << 16;
-              float f;
-              memcpy(&f, &u, 4);
-              dst[(((size_t)l * B + b) * kAudioCtx + t) * d + h * 64 + i] = f;
-            }
-        }
+  if (b0 < 0 || nb <= 0 || b0 + nb > cap_) throw std::runtime_error("cache export: sequence range exceeds the resident capacity");
+  if (n_rows <= 0 || n_rows > T) throw std::runtime_error("cache export: row count out of range");
+  CUDA_CHECK(cudaSetDevice(device_));
+  float* tmp = nullptr;
+  const size_t per = (size_t)nb * n_rows * d;
+  CUDA_CHECK(cudaMalloc(&tmp, per * 4));
+  for (int l = 0; l < L; ++l) {
+    launch_kv_export(cache + ((size_t)l * cap_ + b0) * H * T * 64, tmp, nb, n_rows, T, n_rows, H, stream_);
+    CUDA_CHECK(cudaMemcpyAsync(out + (size_t)l * per, tmp, per * 4, cudaMemcpyDeviceToHost, stream_));
   }
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+  cudaFree(tmp);
+}
+
+void Engine::import_cache(__nv_bfloat16* cache, int T, int B, int n_rows, const float* in) {
+  // in [L][B][T][d] f32 (the reference's full-size tensors); rows [0, n_rows) are loaded
+  const int d = cfg_.d, H = cfg_.n_head, L = cfg_.l_dec;
+  check_batch(B, "cache import");
+  if (n_rows < 0 || n_rows > T) throw std::runtime_error("cache import: row count out of range");
+  if (n_rows == 0) return;
+  CUDA_CHECK(cudaSetDevice(device_));
+  float* tmp = nullptr;
+  const size_t per = (size_t)B * T * d;
+  CUDA_CHECK(cudaMalloc(&tmp, per * 4));
+  for (int l = 0; l < L; ++l) {
+    CUDA_CHECK(cudaMemcpyAsync(tmp, in + (size_t)l * per, per * 4, cudaMemcpyHostToDevice, stream_));
+    launch_kv_import(tmp, cache + (size_t)l * cap_ * H * T * 64, B, n_rows, T, T, H, stream_);
+  }
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+  cudaFree(tmp);
+}
+
+void Engine::read_cross_kv(int b0, int nb, float* cross_k, float* cross_v) const {
+  if (cross_k) export_cache(cross_k_, kAudioCtx, b0, nb, kAudioCtx, cross_k);
+  if (cross_v) export_cache(cross_v_, kAudioCtx, b0, nb, kAudioCtx, cross_v);
+}
+void Engine::load_cross_kv(int B, const float* cross_k, const float* cross_v) {
+  ensure_capacity(B);
+  if (cross_k) import_cache(cross_k_, kAudioCtx, B, kAudioCtx, cross_k);
+  if (cross_v) import_cache(cross_v_, kAudioCtx, B, kAudioCtx, cross_v);
+}
+void Engine::read_self_kv(int B, int n_rows, float* self_k, float* self_v) const {
+  if (self_k) export_cache(self_k_, kTextCtx, 0, B, n_rows, self_k);
+  if (self_v) export_cache(self_v_, kTextCtx, 0, B, n_rows, self_v);
+}
+void Engine::load_self_kv(int B, int n_valid, const float* self_k, const float* self_v) {
+  ensure_capacity(B);
+  if (self_k) import_cache(self_k_, kTextCtx, B, n_valid, self_k);
+  if (self_v) import_cache(self_v_, kTextCtx, B, n_valid, self_v);
 }
 
 void Engine::read_encoder_hidden(int B, float* out) const {

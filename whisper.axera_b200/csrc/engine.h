@@ -55,6 +55,8 @@ struct DecodeOptions {
   const int* forced_tokens = nullptr;       // [B][forced_len] teacher forcing (parity tests) or null
   int forced_len = 0;
   float* logits_out = nullptr;              // host [n_steps][B][n_vocab] (parity tests) or null
+  const int* logit_rows = nullptr;          // with logits_out: only these sequences are copied, logits_out is [n_steps][n_logit_rows][n_vocab]
+  int n_logit_rows = 0;
   bool use_graph = true;
 };
 
@@ -98,7 +100,11 @@ class Engine {
   void decode_reset(int B);
   void decode_step_tokens(int B, const int* tokens_host, int offset, float* logits_host /*[B][n_vocab]*/, float* this_k /*[L][B][d]*/,
                           float* this_v);
-  void read_cross_kv(int B, float* cross_k /*[L][B][1500][d]*/, float* cross_v) const;
+  // caches across the model-ABI boundary, f32 in the reference's layouts (export_onnx.py:587-588, :668-670)
+  void read_cross_kv(int b0, int nb, float* cross_k /*[L][nb][1500][d]*/, float* cross_v) const;  // sequences [b0, b0 + nb)
+  void load_cross_kv(int B, const float* cross_k /*[L][B][1500][d]*/, const float* cross_v);
+  void read_self_kv(int B, int n_rows, float* self_k /*[L][B][n_rows][d]*/, float* self_v) const;
+  void load_self_kv(int B, int n_valid, const float* self_k /*[L][B][448][d]*/, const float* self_v);  // rows [0, n_valid)
   void read_encoder_hidden(int B, float* out /*[B][1500][d]*/) const;  // ln_post input (residual stream) for diagnostics
 
   // ---- whole pipeline with host buffers (copies inside) ----
@@ -116,9 +122,12 @@ class Engine {
  private:
   struct LayerEnc;
   struct LayerDec;
-  struct Workspace;
   void load_weights(const std::string& dir, const std::string& type);
   void free_workspace();
+  void check_batch(int B, const char* what) const;
+  void export_cache(const __nv_bfloat16* cache, int T, int b0, int nb, int n_rows, float* out) const;
+  void import_cache(__nv_bfloat16* cache, int T, int B, int n_rows, const float* in);
+  void allocate_workspace(int new_cap, long new_stride);
   void build_plans();
   void enqueue_decode_step(int B, bool want_logits, bool finalize, int honor_eot, int n_fused = 1);
 
@@ -170,7 +179,7 @@ class Engine {
   std::vector<void*> ws_owned_;
   std::vector<GemmPlan*> plans_;
   // plans
-  GemmPlan *p_conv1_ = nullptr, *p_conv2_ = nullptr, *p_crosskv_ = nullptr, *p_logits_ = nullptr, *p_logits_store_ = nullptr;
+  GemmPlan *p_conv1_ = nullptr, *p_conv2_ = nullptr, *p_crosskv_ = nullptr, *p_logits_ = nullptr;
   struct EncPlans {
     GemmPlan *qkv, *out, *fc1, *fc2;
   };

@@ -142,5 +142,9 @@ void launch_advance_step(int* step, cudaStream_t stream, bool pdl = true);  // *
 void launch_argmax_finalize(const DecodeState& st, const float* part_val, const int* part_idx, int n_tiles, int part_ld, int B,
                             int n_text_ctx, int eot, int honor_eot, int sot_len, cudaStream_t stream);
 int cross_attention_pick_split(int B, int n_head);
+// K/V cache import / export at the model-ABI boundary: f32 token-major [n_seq][T][H*64] (the reference's tensors) <-> the
+// resident bf16 head-major [n_seq][H][T][64]; rows [0, n_rows) of every sequence.
+void launch_kv_import(const float* src, __nv_bfloat16* dst, int n_seq, int n_rows, int T_src, int T_dst, int n_head, cudaStream_t stream);
+void launch_kv_export(const __nv_bfloat16* src, float* dst, int n_seq, int n_rows, int T_src, int T_dst, int n_head, cudaStream_t stream);
 
 }  // namespace b200w

@@ -15,6 +15,7 @@ using namespace b200w;
 struct b200w_engine {
   Engine* eng;
   int last_max_samples = kChunkSamples;
+  std::vector<int> logit_rows;  // b200w_set_logit_rows
 };
 
 namespace {
@@ -132,7 +133,7 @@ int b200w_encoder(b200w_engine* e, const float* mel, int B, float* cross_k, floa
     }
     E.run_encoder(B);
     CUDA_CHECK(cudaStreamSynchronize(E.stream()));
-    if (cross_k || cross_v) E.read_cross_kv(B, cross_k, cross_v);
+    if (cross_k || cross_v) E.read_cross_kv(0, B, cross_k, cross_v);
   });
 }
 
@@ -164,6 +165,54 @@ int b200w_decoder_loop(b200w_engine* e, const int* tokens, int offset, int B, fl
   return guarded([&] { e->eng->decode_step_tokens(B, tokens, offset, logits, this_self_k, this_self_v); });
 }
 
+int b200w_get_cross_kv(b200w_engine* e, int b0, int nb, float* cross_k, float* cross_v) {
+  if (!e || nb <= 0) return -1;
+  return guarded([&] { e->eng->read_cross_kv(b0, nb, cross_k, cross_v); });
+}
+int b200w_set_cross_kv(b200w_engine* e, const float* cross_k, const float* cross_v, int B) {
+  if (!e || B <= 0 || (!cross_k && !cross_v)) return -1;
+  return guarded([&] { e->eng->load_cross_kv(B, cross_k, cross_v); });
+}
+int b200w_set_self_kv(b200w_engine* e, const float* self_k, const float* self_v, int n_valid, int B) {
+  if (!e || B <= 0 || (!self_k && !self_v)) return -1;
+  return guarded([&] { e->eng->load_self_kv(B, n_valid, self_k, self_v); });
+}
+int b200w_get_self_kv(b200w_engine* e, float* self_k, float* self_v, int n_rows, int B) {
+  if (!e || B <= 0) return -1;
+  return guarded([&] {
+    if (B > e->eng->capacity()) throw std::runtime_error("get_self_kv: batch exceeds the resident capacity");
+    e->eng->read_self_kv(B, n_rows, self_k, self_v);
+  });
+}
+
+// The reference's decoder graph, stateless form (export_onnx.py:668-670; the call in Whisper.cpp:306-326): every input tensor is
+// supplied by the caller, the new cache rows are returned.  NULL for a cache means "the resident one".
+int b200w_decoder_step(b200w_engine* e, const int* tokens, const float* self_k, const float* self_v, const float* cross_k,
+                       const float* cross_v, int offset, const int* mask, int B, float* logits, float* this_self_k, float* this_self_v) {
+  if (!e || !tokens || B <= 0) return -1;
+  return guarded([&] {
+    Engine& E = *e->eng;
+    if (offset < 0 || offset >= kTextCtx) throw std::runtime_error("decoder_step: offset out of range");
+    if (mask != nullptr) {
+      // the graph's mask input (1 = masked, export_onnx.py:59-68,:130) is always the causal one the host builds
+      // (Whisper.cpp:201,:253-258: all ones, then mask[offset - 1] = 0 before each step): slots < offset visible
+      for (int j = 0; j < kTextCtx; ++j)
+        if ((mask[j] != 0) != (j >= offset))
+          throw std::runtime_error("decoder_step: only the causal mask of Whisper.cpp:253-258 (mask[j] = j >= offset) is supported; mask[" +
+                                   std::to_string(j) + "] = " + std::to_string(mask[j]) + " at offset " + std::to_string(offset));
+    }
+    if (cross_k || cross_v) E.load_cross_kv(B, cross_k, cross_v);
+    if (self_k || self_v) E.load_self_kv(B, offset, self_k, self_v);
+    E.decode_step_tokens(B, tokens, offset, logits, this_self_k, this_self_v);
+  });
+}
+
+int b200w_set_logit_rows(b200w_engine* e, const int* rows, int n) {
+  if (!e || n < 0 || (n > 0 && !rows)) return -1;
+  e->logit_rows.assign(rows, rows + n);
+  return 0;
+}
+
 int b200w_greedy(b200w_engine* e, int B, const char* language, int max_new_tokens, int honor_eot, const int* forced_tokens, int forced_len,
                  float* logits_out, int* tokens_out, int max_tokens, int* n_tokens_out) {
   if (!e || B <= 0) return -1;
@@ -173,6 +222,7 @@ int b200w_greedy(b200w_engine* e, int B, const char* language, int max_new_token
     o.forced_tokens = forced_tokens;
     o.forced_len = forced_tokens ? forced_len : 0;
     o.logits_out = logits_out;
+    if (logits_out && !e->logit_rows.empty()) o.logit_rows = e->logit_rows.data(), o.n_logit_rows = (int)e->logit_rows.size();
     std::vector<std::vector<int>> toks;
     E.run_decode(B, E.sot_sequence(language ? language : "zh"), o, &toks);
     CUDA_CHECK(cudaStreamSynchronize(E.stream()));
@@ -275,6 +325,19 @@ int b200w_test_base64(const char* in, unsigned char* out, int capacity) {
   const std::string s = base64_decode(in);
   const int n = (int)s.size() < capacity ? (int)s.size() : capacity;
   memcpy(out, s.data(), n);
+  return (int)s.size();
+}
+
+int b200w_test_detokenize(const char* tokens_file, const int* ids, int n, unsigned char* out, int capacity) {
+  if (!tokens_file || !ids || n < 0 || !out) return -1;
+  TokenTable t;
+  std::string err;
+  if (!t.load(tokens_file, &err)) {
+    g_err = err;
+    return -1;
+  }
+  const std::string s = t.detokenize(ids, (size_t)n);
+  memcpy(out, s.data(), std::min<size_t>(s.size(), (size_t)std::max(capacity, 0)));
   return (int)s.size();
 }
 
