@@ -12,10 +12,12 @@ def test_attention_matches_comparator(pkg, B, T, H):
     assert diff <= 2e-2 * max(ref, 1.0)  # both round P and the output to bf16, in different orders
 
 
-# K7 decode cross attention: the streaming kernel (dynamic item claims, rolling loads) against the per-(sequence, head) kernel
-@pytest.mark.parametrize("B,H,T", [(50, 6, 1500), (37, 12, 1500), (128, 12, 1500), (64, 20, 1500), (300, 1, 700), (40, 8, 256)])
-def test_cross_attention_stream_matches_per_head_kernel(pkg, B, H, T):
-    diff, ref = pkg.selftest_cross_attention(B, H, T, seed=B + H + T)
-    print("B=%d H=%d T=%d max|diff| %.4g max|ref| %.3g" % (B, H, T, diff, ref))
-    assert ref > 0.01
-    assert diff <= 1e-2 * max(ref, 1.0)  # same fp32 math, different summation order, bf16 output
+# K7 decode cross attention: the streaming kernel (dynamic item claims, rolling loads) and every cluster split of the small-batch
+# kernel evaluate the same canonical summation order (decode_ops.cu) -> BIT-IDENTICAL outputs, and all of them agree with an
+# fp64 host evaluation within the bf16 rounding of the output.
+@pytest.mark.parametrize("B,H,T", [(50, 6, 1500), (37, 12, 1500), (128, 12, 1500), (64, 20, 1500), (2, 8, 1500), (300, 1, 700), (40, 8, 256), (3, 2, 1024)])
+def test_cross_attention_variants_bit_identical(pkg, B, H, T):
+    diff, ref_err = pkg.selftest_cross_attention(B, H, T, seed=B + H + T)
+    print("B=%d H=%d T=%d max|variant - variant| %.4g max|kernel - fp64 host| %.4g" % (B, H, T, diff, ref_err))
+    assert diff == 0.0, "kernel variants disagree: the output would depend on the batch size"
+    assert ref_err <= 2 ** -7  # |output| stays below ~2 (softmax-weighted average of N(0,1) values); bf16 output rounding is 2^-9 relative

@@ -64,120 +64,6 @@ __device__ __forceinline__ void axpy8(float (&acc)[8], float p, const uint4& v) 
 
 constexpr float kScoreScaleLog2 = 0.125f * 1.4426950408889634f;  // (64^-0.25)^2 * log2(e)
 
-// Attention of ONE query over keys [k_begin, k_end) of a contiguous bf16 [n][64] K and V stream.
-// All NT threads of the CTA participate.  Scores are kept in smem (log2 domain).  Optional extra "current token"
-// (fp32 k1/v1, used by self attention).  Returns through smem: s_out[64] = unnormalised sum_j p_j v_j,
-// *s_m = running max (log2 domain), *s_l = sum_j p_j.
-template <int NT>
-__device__ __forceinline__ void attend_one_query(const float* __restrict__ q_global /*[64] f32*/, const __nv_bfloat16* __restrict__ K,
-                                                 const __nv_bfloat16* __restrict__ V, int k_begin, int k_end, const float* k1,
-                                                 const float* v1, float* s_scores, float* s_red, float* s_out, float* s_ml) {
-  constexpr int NW = NT / 32;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int grp = lane >> 3, sub = lane & 7;  // 4 keys per warp instruction, 8 lanes (16 B each) per key
-  float q[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) q[i] = q_global[sub * 8 + i] * kScoreScaleLog2;
-  const int n = k_end - k_begin;
-
-  // ---- phase 1: scores ----
-  float mx = -INFINITY;
-  constexpr int U = 4;  // independent 16-byte loads in flight per thread
-  for (int jb = warp * 4; jb < n; jb += NW * 4 * U) {  // warp-uniform bounds: the shuffles below need every lane
-    const int j0 = jb + grp;
-    uint4 kv[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int j = j0 + u * NW * 4;
-      kv[u] = j < n ? ld_stream16(K + (long)(k_begin + j) * 64 + sub * 8) : make_uint4(0, 0, 0, 0);
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int j = j0 + u * NW * 4;
-      float s = dot8(kv[u], q);
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      s += __shfl_xor_sync(0xffffffffu, s, 4);
-      if (j < n) {
-        if (sub == 0) s_scores[j] = s;
-        mx = fmaxf(mx, s);
-      }
-    }
-  }
-  float s_cur = -INFINITY;
-  if (k1 != nullptr) {  // current token: fp32 k1 (every thread computes it redundantly: 64 MACs)
-    float a = 0.f;
-#pragma unroll 8
-    for (int i = 0; i < 64; ++i) a = fmaf(q_global[i] * kScoreScaleLog2, k1[i], a);
-    s_cur = a;
-    mx = fmaxf(mx, s_cur);
-  }
-  mx = warp_max(mx);
-  if (lane == 0) s_red[warp] = mx;
-  __syncthreads();
-  float m = s_red[0];
-#pragma unroll
-  for (int w = 1; w < NW; ++w) m = fmaxf(m, s_red[w]);
-  __syncthreads();
-
-  // ---- phase 2: softmax weights and P.V ----
-  float acc[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  float lsum = 0.f;
-  for (int jb = warp * 4; jb < n; jb += NW * 4 * U) {
-    const int j0 = jb + grp;
-    uint4 vv[U];
-    float p[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int j = j0 + u * NW * 4;
-      const bool ok = j < n;
-      vv[u] = ok ? ld_stream16(V + (long)(k_begin + j) * 64 + sub * 8) : make_uint4(0, 0, 0, 0);
-      p[u] = ok ? exp2f(s_scores[j] - m) : 0.f;
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      axpy8(acc, p[u], vv[u]);
-      if (sub == 0) lsum += p[u];
-    }
-  }
-  // reduce the 4 key groups of the warp, then the warps
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
-    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
-  }
-  lsum = warp_sum(lsum);
-  float* s_acc = s_scores;  // scores are dead now; reuse as [NW][64] (+ NW sums)
-  __syncthreads();
-  if (grp == 0) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s_acc[warp * 64 + sub * 8 + i] = acc[i];
-  }
-  if (lane == 0) s_red[warp] = lsum;
-  __syncthreads();
-  if (tid < 64) {
-    float o = 0.f;
-#pragma unroll
-    for (int w = 0; w < NW; ++w) o += s_acc[w * 64 + tid];
-    float l = 0.f;
-#pragma unroll
-    for (int w = 0; w < NW; ++w) l += s_red[w];
-    if (k1 != nullptr) {
-      const float pc = exp2f(s_cur - m);
-      o = fmaf(pc, v1[tid], o);
-      l += pc;
-    }
-    s_out[tid] = o;
-    if (tid == 0) {
-      s_ml[0] = m;
-      s_ml[1] = l;
-    }
-  }
-  __syncthreads();
-}
-
 // ---- embedding -------------------------------------------------------------------------------------------
 __global__ void embed_kernel(const int* __restrict__ step_ptr, const int* __restrict__ tokens, const float* __restrict__ tok_emb,
                              const float* __restrict__ pos_emb, float* __restrict__ x, int d, int n_text_ctx) {
@@ -297,35 +183,151 @@ __global__ void __launch_bounds__(kSelfWarps * 32) self_attention_decode_kernel(
 }
 
 // ---- cross attention ---------------------------------------------------------------------------------------
+// Both kernels below evaluate one (sequence, head) item with EXACTLY the same arithmetic, so that a sequence's tokens do not
+// depend on how many sequences share its batch (VERDICT r01 "output depends on the shard size"):
+//   * 256 threads = 32 key classes (warp w, group g: keys = 4w + g mod 32) x 8 lanes (16 bytes of the 128-byte key each);
+//   * the T keys are cut into SEGMENTS of 256 consecutive keys; inside a segment a thread owns 8 keys (slots u = 0..7, key
+//     256 s + 32 u + 4 w + g) and accumulates p.v over them in slot order starting from zero;
+//   * the softmax maximum is the exact maximum over all keys (order-free), p = exp2(score - max);
+//   * a thread's total is the sum of its segment partials in segment order; totals are reduced over the 4 groups by an
+//     xor-shuffle tree (8, 16), then over the 8 warps in warp order, then divided by the sum reduced the same way.
+// The streaming kernel walks the segments of an item one after the other in one CTA; the split kernel gives each CTA of a
+// thread-block cluster a contiguous range of segments, exchanges the maximum through distributed shared memory and lets
+// cluster rank 0 add the per-thread segment partials in the same order -- bit-identical results, any batch size.
 constexpr int kCrossThreads = 256;
-__global__ void __launch_bounds__(kCrossThreads) cross_attention_decode_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ k,
-                                                                              const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ out,
-                                                                              int n_head, int T, int n_split, float* __restrict__ part_m,
-                                                                              float* __restrict__ part_l, float* __restrict__ part_o) {
-  __shared__ float s_scores[kCrossThreads / 32 * 64 > 1504 ? kCrossThreads / 32 * 64 : 1504];
-  __shared__ float s_red[kCrossThreads / 32];
-  __shared__ float s_out[64];
-  __shared__ float s_ml[2];
+constexpr int kXU = 8;                                        // key slots per thread per segment
+constexpr int kXKeysPerStep = (kCrossThreads / 32) * 4 * kXU;  // 256 keys per segment
+constexpr int kXMaxT = 1536;
+constexpr int kXMaxSegPerCta = 3;                              // split kernel: segments per CTA (cluster of >= 2 CTAs)
+
+// Small batches: cluster of n_split CTAs per (sequence, head), n_split dividing the segment count.
+__global__ void __launch_bounds__(kCrossThreads)
+cross_attention_split_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
+                             __nv_bfloat16* __restrict__ out, int T, int evict_first) {
+  constexpr int NW = kCrossThreads / 32;
+  __shared__ float s_scores[kXMaxSegPerCta * kXKeysPerStep];
+  __shared__ __align__(16) float s_part[kXMaxSegPerCta][8][kCrossThreads];  // per-thread segment partials of p.v (read by rank 0)
+  __shared__ float s_lpart[kXMaxSegPerCta][kCrossThreads / 8];              // per key-class segment partials of sum p
+  __shared__ float s_acc[NW * 64];
+  __shared__ float s_redm[NW], s_redl[NW];
+  __shared__ float s_max;                                                   // this CTA's maximum (read by every rank)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grp = lane >> 3, sub = lane & 7;
+  const int nseg = (T + kXKeysPerStep - 1) / kXKeysPerStep;
+  const uint32_t n_split = cluster_nctarank(), rank = cluster_ctarank();
+  const int seg_per = nseg / (int)n_split;           // the launcher picks n_split dividing nseg
+  const int seg0 = (int)rank * seg_per;
+  const int item = blockIdx.x / n_split;             // (sequence, head) in the cache's own order
+  const int key0 = warp * 4 + grp;
+  const uint64_t pol = l2_evict_first_policy(evict_first != 0);
+  const __nv_bfloat16* kb = k + (long)item * T * 64 + sub * 8;
+  const __nv_bfloat16* vb = v + (long)item * T * 64 + sub * 8;
+
+  // K of the first segment is requested before the dependency wait: the cross K/V cache was written by the encoder long ago,
+  // only q depends on the predecessor kernel
+  uint4 kv[kXU];
+  {
+    const int j0 = seg0 * kXKeysPerStep + key0;
+#pragma unroll
+    for (int u = 0; u < kXU; ++u) kv[u] = (j0 + 32 * u < T) ? ld_stream16_ef(kb + (long)(j0 + 32 * u) * 64, pol) : make_uint4(0, 0, 0, 0);
+  }
   pdl_wait();
-  const int h = blockIdx.x / n_split, sp = blockIdx.x % n_split;
-  const int b = blockIdx.y;
-  const int d = n_head * 64;
-  const long kv_off = ((long)b * n_head + h) * T * 64;
-  const int per = (T + n_split - 1) / n_split;
-  const int k_begin = sp * per, k_end = min(T, k_begin + per);
-  attend_one_query<kCrossThreads>(q + (long)b * d + h * 64, k + kv_off, v + kv_off, k_begin, k_end, nullptr, nullptr, s_scores, s_red,
-                                  s_out, s_ml);
-  pdl_launch_dependents();  // multi-wave kernel: let the successor start only in this CTA's tail
-  if (n_split == 1) {
-    if (threadIdx.x < 64) out[(long)b * d + h * 64 + threadIdx.x] = __float2bfloat16_rn(s_out[threadIdx.x] / s_ml[1]);
-  } else {
-    const long pi = ((long)b * n_head + h) * n_split + sp;
-    if (threadIdx.x < 64) part_o[pi * 64 + threadIdx.x] = s_out[threadIdx.x];
-    if (threadIdx.x == 0) {
-      part_m[pi] = s_ml[0];
-      part_l[pi] = s_ml[1];
+  float qr[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) qr[i] = q[(long)item * 64 + sub * 8 + i] * kScoreScaleLog2;
+
+  // ---- phase 1: scores of this CTA's segments, local maximum ----
+  float mx = -INFINITY;
+  for (int sl = 0; sl < seg_per; ++sl) {
+    const int j0 = (seg0 + sl) * kXKeysPerStep + key0;
+    const bool last = sl + 1 == seg_per;
+    // next loads: the following K segment, or the first V segment
+    const __nv_bfloat16* nb = last ? vb : kb;
+    const int nj = (last ? seg0 : seg0 + sl + 1) * kXKeysPerStep + key0;
+#pragma unroll
+    for (int u = 0; u < kXU; ++u) {
+      const int j = j0 + 32 * u;
+      float sc = dot8(kv[u], qr);
+      kv[u] = (nj + 32 * u < T) ? ld_stream16_ef(nb + (long)(nj + 32 * u) * 64, pol) : make_uint4(0, 0, 0, 0);
+      sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+      sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+      sc += __shfl_xor_sync(0xffffffffu, sc, 4);
+      if (j < T) {
+        if (sub == 0) s_scores[sl * kXKeysPerStep + 32 * u + key0] = sc;
+        mx = fmaxf(mx, sc);
+      }
     }
   }
+  mx = warp_max(mx);
+  if (lane == 0) s_redm[warp] = mx;
+  __syncthreads();
+  if (tid == 0) {
+    float m = s_redm[0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) m = fmaxf(m, s_redm[w]);
+    s_max = m;
+  }
+  cluster_sync_all();  // every rank's s_max is written (also orders s_scores / s_redm within the CTA)
+  float m = -INFINITY;
+  for (uint32_t r = 0; r < n_split; ++r) m = fmaxf(m, dsmem_ld_f32(dsmem_addr(&s_max, r)));  // exact, order-free
+
+  // ---- phase 2: softmax weights and P.V, one partial per segment ----
+  for (int sl = 0; sl < seg_per; ++sl) {
+    const int j0 = (seg0 + sl) * kXKeysPerStep + key0;
+    const bool last = sl + 1 == seg_per;
+    const int nj = (seg0 + sl + 1) * kXKeysPerStep + key0;
+    float seg[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) seg[i] = 0.f;
+    float lseg = 0.f;
+#pragma unroll
+    for (int u = 0; u < kXU; ++u) {
+      const int j = j0 + 32 * u;
+      const float pw = j < T ? exp2f(s_scores[sl * kXKeysPerStep + 32 * u + key0] - m) : 0.f;
+      axpy8(seg, pw, kv[u]);
+      kv[u] = (!last && nj + 32 * u < T) ? ld_stream16_ef(vb + (long)(nj + 32 * u) * 64, pol) : make_uint4(0, 0, 0, 0);
+      if (sub == 0) lseg += pw;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_part[sl][i][tid] = seg[i];
+    if (sub == 0) s_lpart[sl][tid >> 3] = lseg;
+  }
+  pdl_launch_dependents();
+  cluster_sync_all();  // all partials of all ranks are in shared memory
+  if (rank == 0) {
+    // thread totals in segment order (rank r holds segments r * seg_per ..), exactly what the streaming kernel accumulates
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    float lsum = 0.f;
+    for (uint32_t r = 0; r < n_split; ++r) {
+      const uint32_t pa = dsmem_addr(&s_part[0][0][0], r), la = dsmem_addr(&s_lpart[0][0], r);
+      for (int sl = 0; sl < seg_per; ++sl) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += dsmem_ld_f32(pa + (uint32_t)(((sl * 8 + i) * kCrossThreads + tid) * 4));
+        if (sub == 0) lsum += dsmem_ld_f32(la + (uint32_t)((sl * (kCrossThreads / 8) + (tid >> 3)) * 4));
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
+      acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+    }
+    lsum = warp_sum(lsum);
+    if (grp == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s_acc[warp * 64 + sub * 8 + i] = acc[i];
+    }
+    if (lane == 0) s_redl[warp] = lsum;
+    __syncthreads();
+    if (tid < 64) {
+      float o = 0.f, l = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) o += s_acc[w * 64 + tid], l += s_redl[w];
+      out[(long)item * 64 + tid] = __float2bfloat16_rn(o / l);  // out is [B][H*64]
+    }
+  }
+  cluster_sync_all();  // nobody leaves (and frees its shared memory) before rank 0 has read the partials
 }
 
 // Streaming variant for large batches.  A single resident wave of CTAs (at most three per SM, 64 registers) each works
@@ -335,9 +337,6 @@ __global__ void __launch_bounds__(kCrossThreads) cross_attention_decode_kernel(c
 // the whole grid is dispatched at once and leaves ~16 K registers and most of the shared memory of every SM free, the
 // short kernels of the other micro-batch (192-thread tcgen05 GEMM CTAs, LayerNorm, self attention) are placed next to
 // it immediately instead of queueing behind undispatched CTAs.
-constexpr int kXU = 8;                                        // rolling loads per thread
-constexpr int kXKeysPerStep = (kCrossThreads / 32) * 4 * kXU;  // 256 keys per step
-constexpr int kXMaxT = 1536;
 __global__ void __maxnreg__(64)
 cross_attention_stream_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
                               __nv_bfloat16* __restrict__ out, int T, int n_items, int* __restrict__ work /*[2]: next item, CTAs done*/,
@@ -346,6 +345,7 @@ cross_attention_stream_kernel(const float* __restrict__ q, const __nv_bfloat16* 
   __shared__ float s_scores[kXMaxT];
   __shared__ float s_acc[NW * 64];
   __shared__ float s_redm[NW], s_redl[NW];
+  __shared__ float s_q[2][64];
   __shared__ int s_item[2];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int grp = lane >> 3, sub = lane & 7;  // 4 keys per warp instruction, 8 lanes (16 B each) per key
@@ -381,61 +381,71 @@ cross_attention_stream_kernel(const float* __restrict__ q, const __nv_bfloat16* 
 #pragma unroll
     for (int i = 0; i < 8; ++i) qr[i] = q[(long)item * 64 + sub * 8 + i] * kScoreScaleLog2;  // q is [B][H*64]: item * 64
 
-    float mx = -INFINITY, m = 0.f, lsum = 0.f;
-    float acc[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
     int next_item = n_items;
     for (;;) {
-      for (int st = 0; st < spi; ++st) {
-        // the step after this one (its loads are issued slot by slot while this step is consumed)
+      // ---- K phase: scores (log2 domain) into smem, running maximum.  The step after each one -- next K segment, then the
+      // first V segment -- is requested slot by slot while the current one is consumed ----
+      float mx = -INFINITY;
+      for (int st = 0; st < nk; ++st) {
+        const __nv_bfloat16* np = step_ptr(item, st + 1);
+        const int nj = step_key(st + 1);
+        const int j0 = step_key(st);
+#pragma unroll
+        for (int u = 0; u < kXU; ++u) {
+          const int j = j0 + 32 * u;
+          float sc = dot8(kv[u], qr);
+          kv[u] = (nj + 32 * u < T) ? ld_stream16_ef(np + u * 32 * 64, pol) : make_uint4(0, 0, 0, 0);
+          sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+          sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+          sc += __shfl_xor_sync(0xffffffffu, sc, 4);
+          if (j < T) {
+            if (sub == 0) s_scores[j] = sc;
+            mx = fmaxf(mx, sc);
+          }
+        }
+      }
+      // phase boundary: block maximum (the first V loads are already in flight)
+      mx = warp_max(mx);
+      if (lane == 0) s_redm[warp] = mx;
+      if (tid == 0) s_item[par ^ 1] = atomicAdd(&work[0], 1);  // claim the next item while V streams
+      __syncthreads();
+      float m = s_redm[0];
+#pragma unroll
+      for (int w = 1; w < NW; ++w) m = fmaxf(m, s_redm[w]);
+      next_item = s_item[par ^ 1];
+      // the next item's query goes to shared memory asynchronously while V streams (the registers hold the segment partials
+      // now); it is picked up when that item's K phase starts
+      if (next_item < n_items && tid < 64) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&s_q[par ^ 1][tid])), "l"(q + (long)next_item * 64 + tid) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+      // ---- V phase: softmax weights and P.V; every 256-key segment is ONE partial added to the thread's total (the canonical
+      // summation order shared with cross_attention_split_kernel) ----
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      float lsum = 0.f;
+      for (int st = nk; st < spi; ++st) {
         const bool same = st + 1 < spi;
         const bool has_next = same || next_item < n_items;
         const __nv_bfloat16* np = has_next ? step_ptr(same ? item : next_item, same ? st + 1 : 0) : k;
         const int nj = has_next ? step_key(same ? st + 1 : 0) : T;  // T: every slot predicated off
         const int j0 = step_key(st);
-        if (st < nk) {
-          // ---- K step: scores (log2 domain) into smem, running maximum ----
+        float seg[8];
 #pragma unroll
-          for (int u = 0; u < kXU; ++u) {
-            const int j = j0 + 32 * u;
-            float sc = dot8(kv[u], qr);
-            kv[u] = (nj + 32 * u < T) ? ld_stream16_ef(np + u * 32 * 64, pol) : make_uint4(0, 0, 0, 0);
-            sc += __shfl_xor_sync(0xffffffffu, sc, 1);
-            sc += __shfl_xor_sync(0xffffffffu, sc, 2);
-            sc += __shfl_xor_sync(0xffffffffu, sc, 4);
-            if (j < T) {
-              if (sub == 0) s_scores[j] = sc;
-              mx = fmaxf(mx, sc);
-            }
-          }
-          if (st == nk - 1) {  // phase boundary: block maximum (the first V loads are already in flight)
-            mx = warp_max(mx);
-            if (lane == 0) s_redm[warp] = mx;
-            if (tid == 0) s_item[par ^ 1] = atomicAdd(&work[0], 1);  // claim the next item while V streams
-            __syncthreads();
-            m = s_redm[0];
+        for (int i = 0; i < 8; ++i) seg[i] = 0.f;
+        float lseg = 0.f;
 #pragma unroll
-            for (int w = 1; w < NW; ++w) m = fmaxf(m, s_redm[w]);
-            mx = -INFINITY;
-            next_item = s_item[par ^ 1];
-            // q is dead from here on: fetch the next item's query so that it is there when its K phase starts
-            if (next_item < n_items) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) qr[i] = q[(long)next_item * 64 + sub * 8 + i] * kScoreScaleLog2;
-            }
-          }
-        } else {
-          // ---- V step: softmax weights and P.V ----
-#pragma unroll
-          for (int u = 0; u < kXU; ++u) {
-            const int j = j0 + 32 * u;
-            const float pw = j < T ? exp2f(s_scores[j] - m) : 0.f;
-            axpy8(acc, pw, kv[u]);
-            kv[u] = (nj + 32 * u < T) ? ld_stream16_ef(np + u * 32 * 64, pol) : make_uint4(0, 0, 0, 0);
-            if (sub == 0) lsum += pw;
-          }
+        for (int u = 0; u < kXU; ++u) {
+          const int j = j0 + 32 * u;
+          const float pw = j < T ? exp2f(s_scores[j] - m) : 0.f;
+          axpy8(seg, pw, kv[u]);
+          kv[u] = (nj + 32 * u < T) ? ld_stream16_ef(np + u * 32 * 64, pol) : make_uint4(0, 0, 0, 0);
+          if (sub == 0) lseg += pw;
         }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += seg[i];
+        lsum += lseg;
       }
       // item done: reduce over key groups and warps, write the head's output (the next item's K loads are in flight)
 #pragma unroll
@@ -449,6 +459,7 @@ cross_attention_stream_kernel(const float* __restrict__ q, const __nv_bfloat16* 
         for (int i = 0; i < 8; ++i) s_acc[warp * 64 + sub * 8 + i] = acc[i];
       }
       if (lane == 0) s_redl[warp] = lsum;
+      asm volatile("cp.async.wait_all;" ::: "memory");  // this thread's piece of the next query has landed
       __syncthreads();
       if (tid < 64) {
         float o = 0.f, l = 0.f;
@@ -456,13 +467,13 @@ cross_attention_stream_kernel(const float* __restrict__ q, const __nv_bfloat16* 
         for (int w = 0; w < NW; ++w) o += s_acc[w * 64 + tid], l += s_redl[w];
         out[(long)item * 64 + tid] = __float2bfloat16_rn(o / l);  // out is [B][H*64]
       }
+      if (next_item < n_items) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) qr[i] = s_q[par ^ 1][sub * 8 + i] * kScoreScaleLog2;
+      }
       __syncthreads();  // s_acc / s_redl / s_scores are rewritten by the next item
       if (next_item >= n_items) break;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-      lsum = 0.f;
       item = next_item;
-      next_item = n_items;
       par ^= 1;
     }
   }
@@ -476,23 +487,6 @@ cross_attention_stream_kernel(const float* __restrict__ q, const __nv_bfloat16* 
       __threadfence();
     }
   }
-}
-
-__global__ void cross_attention_combine_kernel(const float* __restrict__ part_m, const float* __restrict__ part_l,
-                                               const float* __restrict__ part_o, __nv_bfloat16* __restrict__ out, int n_head, int n_split) {
-  pdl_wait();
-  pdl_launch_dependents();
-  const int h = blockIdx.x, b = blockIdx.y, t = threadIdx.x;  // 64 threads
-  const long base = ((long)b * n_head + h) * n_split;
-  float m = -INFINITY;
-  for (int s = 0; s < n_split; ++s) m = fmaxf(m, part_m[base + s]);
-  float o = 0.f, l = 0.f;
-  for (int s = 0; s < n_split; ++s) {
-    const float w = exp2f(part_m[base + s] - m);
-    o = fmaf(w, part_o[(base + s) * 64 + t], o);
-    l = fmaf(w, part_l[base + s], l);
-  }
-  out[((long)b * n_head + h) * 64 + t] = __float2bfloat16_rn(o / l);
 }
 
 // ---- argmax finalize + loop bookkeeping --------------------------------------------------------------------
@@ -594,30 +588,41 @@ void launch_self_attention_decode(const float* qkv, __nv_bfloat16* k_cache, __nv
              v_cache, step, out, n_pairs, n_head, n_ctx);
 }
 
-int cross_attention_pick_split(int B, int n_head) {
-  // enough CTAs for ~4 per SM; a single split once the batch provides them
-  static const int forced = getenv("B200W_CROSS_SPLIT") ? atoi(getenv("B200W_CROSS_SPLIT")) : 0;
-  if (forced > 0) return forced;
-  int split = 1;
-  while (B * n_head * split < 4 * kNumSMs && split < 8) split *= 2;
-  return split;
+int cross_attention_pick_split(int B, int n_head, int T) {
+  // 0 = streaming kernel (one resident wave, items claimed dynamically); n > 0 = cluster of n CTAs per item.  Few items:
+  // split every item over as many CTAs as it has segments so that enough loads are in flight; the arithmetic is the same.
+  static const int forced = getenv("B200W_CROSS_SPLIT") ? atoi(getenv("B200W_CROSS_SPLIT")) : -1;
+  static const bool no_stream = getenv("B200W_NO_CROSS_STREAM") != nullptr;
+  const int nseg = (T + kXKeysPerStep - 1) / kXKeysPerStep;
+  const int n_items = B * n_head;
+  if (T > kXMaxT) throw CudaError("cross attention: more keys than the kernels are sized for");
+  auto valid = [&](int n) { return n >= 1 && n <= 8 && nseg % n == 0 && nseg / n <= kXMaxSegPerCta && !(n == 1 && nseg > kXMaxSegPerCta); };
+  if (forced == 0) return 0;
+  if (forced > 0 && valid(forced)) return forced;
+  if (!no_stream && n_items >= 2 * kNumSMs) return 0;
+  int best = 0;
+  for (int n = 1; n <= 8; ++n) {
+    if (!valid(n)) continue;
+    best = n;
+    if (n_items * n >= 2 * kNumSMs) break;
+  }
+  return best;  // 0 only if no valid split exists (then the streaming kernel runs whatever the batch)
 }
 
 void launch_cross_attention_decode(const float* q, const __nv_bfloat16* k, const __nv_bfloat16* v, __nv_bfloat16* out, int B, int n_head,
-                                   int T, int n_split, float* part_m, float* part_l, float* part_o, cudaStream_t stream, bool pdl, int* work) {
-  static const bool no_stream = getenv("B200W_NO_CROSS_STREAM") != nullptr;
+                                   int T, int n_split, cudaStream_t stream, bool pdl, int* work) {
   const int n_items = B * n_head;
-  if (!no_stream && work != nullptr && n_split == 1 && n_items >= 2 * kNumSMs && T <= kXMaxT) {
+  static const int evict_first = getenv("B200W_NO_EVICT_FIRST") == nullptr;
+  if (n_split <= 0) {
+    if (work == nullptr) throw CudaError("cross attention: the streaming kernel needs its work counters");
     // single resident wave: three CTAs on every SM, items claimed dynamically
     static const int ctas_per_sm = getenv("B200W_CROSS_CTAS_PER_SM") ? atoi(getenv("B200W_CROSS_CTAS_PER_SM")) : 3;
     const int grid = std::min(n_items, ctas_per_sm * kNumSMs);
-    static const int evict_first = getenv("B200W_NO_EVICT_FIRST") == nullptr;
     launch_k(pdl, cross_attention_stream_kernel, dim3(grid), dim3(kCrossThreads), 0, stream, q, k, v, out, T, n_items, work, evict_first);
     return;
   }
-  dim3 grid(n_head * n_split, B);
-  launch_k(pdl, cross_attention_decode_kernel, grid, dim3(kCrossThreads), 0, stream, q, k, v, out, n_head, T, n_split, part_m, part_l, part_o);
-  if (n_split > 1) launch_pdl(cross_attention_combine_kernel, dim3(n_head, B), dim3(64), 0, stream, part_m, part_l, part_o, out, n_head, n_split);
+  launch_kc(pdl, n_split, cross_attention_split_kernel, dim3(n_items * n_split), dim3(kCrossThreads), 0, stream, q, k, v, out, T,
+            n_split == 1 ? 0 : evict_first);
 }
 
 void decode_ops_set_attributes() {}

@@ -378,7 +378,7 @@ void Engine::free_workspace() {
   // the engine is EMPTY from here until ensure_capacity() has rebuilt everything: a failed re-allocation must not leave
   // capacities that describe freed memory
   cap_ = 0, pcm_stride_ = 0, enc_sub_ = 0, dec_rows_pad_ = 0;
-  pcm_ = mel_ = utt_max_ = x_enc_ = x_dec_ = qkv_dec_ = q_dec_ = logits_ = part_val_ = part_m_ = part_l_ = part_o_ = nullptr;
+  pcm_ = mel_ = utt_max_ = x_enc_ = x_dec_ = qkv_dec_ = q_dec_ = logits_ = part_val_ = nullptr;
   n_samples_ = part_idx_ = cross_work_ = step_ctr_ = nullptr;
   mel_tm_ = conv1_out_ = h_enc_ = qkv_enc_ = attn_enc_ = mlp_enc_ = cross_k_ = cross_v_ = self_k_ = self_v_ = nullptr;
   h_dec_ = attn_dec_ = mlp_dec_ = nullptr;
@@ -438,10 +438,6 @@ void Engine::allocate_workspace(int new_cap, long new_stride) {
   logits_tiles_ = vocab_pad_ / 128 * 2;  // arg-max partials: two column halves per 128-wide logits tile (gemm epilogue)
   part_val_ = dev_alloc<float>(o, (size_t)cap_ * logits_tiles_);
   part_idx_ = dev_alloc<int>(o, (size_t)cap_ * logits_tiles_);
-  const size_t np = (size_t)cap_ * H * 8;
-  part_m_ = dev_alloc<float>(o, np);
-  part_l_ = dev_alloc<float>(o, np);
-  part_o_ = dev_alloc<float>(o, np * 64);
   cross_work_ = dev_alloc<int>(o, (size_t)cfg_.l_dec * 4 * 2 + 2);  // item counters of the streaming cross-attention launches
   step_ctr_ = dev_alloc<int>(o, 4);  // one step counter per micro-batch (they advance independently inside a graph)
   st_.step = step_ctr_;
@@ -653,9 +649,8 @@ void Engine::enqueue_decode_step(int B, bool want_logits, bool finalize, int hon
       }
       for (int i = 0; i < n_mb; ++i) {
         const MB& m = mb[i];
-        const int n_split = cross_attention_pick_split(m.nb, H);
+        const int n_split = cross_attention_pick_split(m.nb, H, kAudioCtx);
         const size_t ckv_off = ((size_t)l * cap_ + m.b0) * H * kAudioCtx * 64;
-        const size_t po = (size_t)m.b0 * H * 8;
         if (chain) {
           // the cross-attention kernels take turns on HBM: micro-batch i waits for micro-batch i-1's kernel of this layer,
           // micro-batch 0 for the last micro-batch's kernel of the previous layer
@@ -665,11 +660,10 @@ void Engine::enqueue_decode_step(int B, bool want_logits, bool finalize, int hon
         {
           ScopedLaunchPriority low(0);
           launch_cross_attention_decode(q_dec_ + (size_t)m.b0 * d, cross_k_ + ckv_off, cross_v_ + ckv_off, attn_dec_ + (size_t)m.b0 * d,
-                                        m.nb, H, kAudioCtx, n_split, part_m_ + po, part_l_ + po, part_o_ + po * 64, m.s, /*pdl=*/!chain,
-                                        cross_work_ + (l * 4 + i) * 2);
+                                        m.nb, H, kAudioCtx, n_split, m.s, /*pdl=*/!chain, cross_work_ + (l * 4 + i) * 2);
         }
         if (chain) CUDA_CHECK(cudaEventRecord(cross_event(l, i), m.s));
-        launches_ += 1 + (n_split > 1 ? 1 : 0);
+        launches_ += 1;
       }
       for (int i = 0; i < n_mb; ++i) {
         const MB& m = mb[i];
@@ -710,12 +704,12 @@ void Engine::enqueue_decode_step(int B, bool want_logits, bool finalize, int hon
 void Engine::run_cross_attention_only(int B) {
   check_batch(B, "run_cross_attention_only");
   const int H = cfg_.n_head;
-  const int n_split = cross_attention_pick_split(B, H);
+  const int n_split = cross_attention_pick_split(B, H, kAudioCtx);
   for (int l = 0; l < cfg_.l_dec; ++l) {
     const size_t ckv_off = (size_t)l * cap_ * H * kAudioCtx * 64;
-    launch_cross_attention_decode(q_dec_, cross_k_ + ckv_off, cross_v_ + ckv_off, attn_dec_, B, H, kAudioCtx, n_split, part_m_, part_l_,
-                                  part_o_, stream_, true, cross_work_ + (size_t)cfg_.l_dec * 4 * 2);
-    launches_ += 1 + (n_split > 1 ? 1 : 0);
+    launch_cross_attention_decode(q_dec_, cross_k_ + ckv_off, cross_v_ + ckv_off, attn_dec_, B, H, kAudioCtx, n_split, stream_, true,
+                                  cross_work_ + (size_t)cfg_.l_dec * 4 * 2);
+    launches_ += 1;
   }
 }
 

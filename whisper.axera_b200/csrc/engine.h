@@ -171,7 +171,7 @@ class Engine {
   __nv_bfloat16 *cross_k_ = nullptr, *cross_v_ = nullptr, *self_k_ = nullptr, *self_v_ = nullptr;
   float *x_dec_ = nullptr, *qkv_dec_ = nullptr, *q_dec_ = nullptr, *logits_ = nullptr;
   __nv_bfloat16 *h_dec_ = nullptr, *attn_dec_ = nullptr, *mlp_dec_ = nullptr;
-  float *part_val_ = nullptr, *part_m_ = nullptr, *part_l_ = nullptr, *part_o_ = nullptr;
+  float* part_val_ = nullptr;
   int* part_idx_ = nullptr;
   DecodeState st_{};
   int dec_rows_pad_ = 0;

@@ -132,16 +132,15 @@ void launch_embed(const DecodeState& st, const float* tok_emb, const float* pos_
 void launch_self_attention_decode(const float* qkv, __nv_bfloat16* k_cache, __nv_bfloat16* v_cache, const int* step,
                                   __nv_bfloat16* out, int B, int n_head, int n_ctx, cudaStream_t stream);
 // cross attention: q f32 [B][d] over bf16 head-major K/V [B][H][T][64]; out bf16 [B][d].
-// part_* are workspaces for the split-T variant ([B*H*n_split] each, o is [..][64]).
-// work: two zero-initialised ints owned by this launch site (large batches: streaming kernel with dynamic item claims).
+// n_split from cross_attention_pick_split(): 0 = streaming kernel (needs `work`: two zero-initialised ints owned by this launch
+// site), n > 0 = thread-block cluster of n CTAs per (sequence, head).  Every variant computes bit-identical results.
 void launch_cross_attention_decode(const float* q, const __nv_bfloat16* k, const __nv_bfloat16* v, __nv_bfloat16* out, int B,
-                                   int n_head, int T, int n_split, float* part_m, float* part_l, float* part_o,
-                                   cudaStream_t stream, bool pdl = true, int* work = nullptr);
+                                   int n_head, int T, int n_split, cudaStream_t stream, bool pdl = true, int* work = nullptr);
 // reduces the argmax partials, applies teacher forcing / EOT bookkeeping, stores the next token
 void launch_advance_step(int* step, cudaStream_t stream, bool pdl = true);  // *step += 1 (once per decoder step)
 void launch_argmax_finalize(const DecodeState& st, const float* part_val, const int* part_idx, int n_tiles, int part_ld, int B,
                             int n_text_ctx, int eot, int honor_eot, int sot_len, cudaStream_t stream);
-int cross_attention_pick_split(int B, int n_head);
+int cross_attention_pick_split(int B, int n_head, int T);
 // K/V cache import / export at the model-ABI boundary: f32 token-major [n_seq][T][H*64] (the reference's tensors) <-> the
 // resident bf16 head-major [n_seq][H][T][64]; rows [0, n_rows) of every sequence.
 void launch_kv_import(const float* src, __nv_bfloat16* dst, int n_seq, int n_rows, int T_src, int T_dst, int n_head, cudaStream_t stream);
