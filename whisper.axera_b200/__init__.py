@@ -19,7 +19,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libax_whisper.so")
+# B200W_LIB: another build of the same library (A/B measurements of two revisions on one GPU box, scripts/ab_build.sh)
+LIB_PATH = os.environ.get("B200W_LIB") or os.path.join(_HERE, "libax_whisper.so")
 N_FRAMES = 3000
 N_AUDIO_CTX = 1500
 N_TEXT_CTX = 448

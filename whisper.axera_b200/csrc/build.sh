@@ -1,5 +1,5 @@
 #!/bin/bash
-# Builds libax_whisper.so (sm_100a only) and whisper_cli in-tree. nvcc cross-compiles without a GPU.
+# Builds libax_whisper.so (sm_100a only), whisper_cli and whisper_srv in-tree. nvcc cross-compiles without a GPU.
 set -euo pipefail
 cd "$(dirname "$0")"
 OUT=${OUT:-..}
@@ -21,4 +21,5 @@ done
 for p in "${pids[@]}"; do wait $p; done
 $NVCC -shared -o $OUT/libax_whisper.so $OBJ/*.o -lcudart_static -ldl -lpthread -lrt -Xcompiler -static-libstdc++,-static-libgcc -Xlinker --exclude-libs=ALL
 g++ -O2 -std=c++17 whisper_cli.cpp host_utils.cpp -o $OUT/whisper_cli -L$OUT -lax_whisper -Wl,-rpath,'$ORIGIN' -static-libstdc++ -static-libgcc
-echo "built $OUT/libax_whisper.so $OUT/whisper_cli"
+g++ -O2 -std=c++17 -pthread whisper_srv.cpp -o $OUT/whisper_srv -L$OUT -lax_whisper -Wl,-rpath,'$ORIGIN' -static-libstdc++ -static-libgcc
+echo "built $OUT/libax_whisper.so $OUT/whisper_cli $OUT/whisper_srv"
