@@ -90,6 +90,10 @@ B200W_API int b200w_get_self_kv(b200w_engine* e, float* self_k, float* self_v, i
 B200W_API int b200w_decoder_step(b200w_engine* e, const int* tokens, const float* self_k, const float* self_v, const float* cross_k,
                                  const float* cross_v, int offset, const int* mask, int B, float* logits, float* this_self_k,
                                  float* this_self_v);
+/* EOT handling of the greedy loop: finished sequences are dropped from the decoder's slot list at the 16-step polls (the
+ * remaining steps cost what the still-running sequences cost).  *compactions = how often that happened since the engine was
+ * created, *last_active = sequences still decoding when the last greedy loop stopped. */
+B200W_API int b200w_decode_stats(const b200w_engine* e, long* compactions, int* last_active);
 /* With logits_out in b200w_greedy: copy only these sequences' logits, logits_out becomes [max_new_tokens][n][n_vocab]
  * (n = 0 restores "all sequences"). */
 B200W_API int b200w_set_logit_rows(b200w_engine* e, const int* rows, int n);

@@ -52,7 +52,7 @@ EXPORTED_SYMBOLS = [
     "b200w_last_error", "b200w_engine_create", "b200w_engine_destroy", "b200w_get_dims", "b200w_sot_sequence",
     "b200w_logmel", "b200w_encoder", "b200w_decoder_main", "b200w_decoder_loop", "b200w_greedy", "b200w_transcribe",
     "b200w_upload_pcm", "b200w_transcribe_resident", "b200w_time_stage", "b200w_selftest_gemm", "b200w_mel_tables",
-    "b200w_get_cross_kv", "b200w_set_cross_kv", "b200w_set_self_kv", "b200w_get_self_kv", "b200w_decoder_step", "b200w_set_logit_rows",
+    "b200w_get_cross_kv", "b200w_set_cross_kv", "b200w_set_self_kv", "b200w_get_self_kv", "b200w_decoder_step", "b200w_set_logit_rows", "b200w_decode_stats",
     "b200w_test_parse_config", "b200w_test_load_wav", "b200w_test_base64", "b200w_test_detokenize", "b200w_selftest_attention", "b200w_selftest_cross_attention",
 ]
 
@@ -90,12 +90,13 @@ def load_library():
     lib.b200w_encoder.argtypes = [vp, _c_float_p, ci, _c_float_p, _c_float_p]
     lib.b200w_decoder_main.argtypes = [vp, _c_int_p, ci, ci, _c_float_p, _c_float_p, _c_float_p]
     lib.b200w_decoder_loop.argtypes = [vp, _c_int_p, ci, ci, _c_float_p, _c_float_p, _c_float_p]
-    lib.b200w_get_cross_kv.argtypes = [vp, ci, ci, _c_float_p, _c_float_p]
-    lib.b200w_set_cross_kv.argtypes = [vp, _c_float_p, _c_float_p, ci]
-    lib.b200w_set_self_kv.argtypes = [vp, _c_float_p, _c_float_p, ci, ci]
-    lib.b200w_get_self_kv.argtypes = [vp, _c_float_p, _c_float_p, ci, ci]
-    lib.b200w_decoder_step.argtypes = [vp, _c_int_p, _c_float_p, _c_float_p, _c_float_p, _c_float_p, ci, _c_int_p, ci, _c_float_p, _c_float_p, _c_float_p]
-    lib.b200w_set_logit_rows.argtypes = [vp, _c_int_p, ci]
+    _sig(lib, "b200w_get_cross_kv", [vp, ci, ci, _c_float_p, _c_float_p])
+    _sig(lib, "b200w_set_cross_kv", [vp, _c_float_p, _c_float_p, ci])
+    _sig(lib, "b200w_set_self_kv", [vp, _c_float_p, _c_float_p, ci, ci])
+    _sig(lib, "b200w_get_self_kv", [vp, _c_float_p, _c_float_p, ci, ci])
+    _sig(lib, "b200w_decoder_step", [vp, _c_int_p, _c_float_p, _c_float_p, _c_float_p, _c_float_p, ci, _c_int_p, ci, _c_float_p, _c_float_p, _c_float_p])
+    _sig(lib, "b200w_set_logit_rows", [vp, _c_int_p, ci])
+    _sig(lib, "b200w_decode_stats", [vp, ctypes.POINTER(cl), _c_int_p])
     lib.b200w_greedy.argtypes = [vp, ci, cp, ci, ci, _c_int_p, ci, _c_float_p, _c_int_p, ci, _c_int_p]
     lib.b200w_transcribe.argtypes = [vp, _c_float_p, cl, _c_int_p, ci, cp, ci, ci, _c_int_p, ci, _c_int_p, ctypes.POINTER(Times)]
     lib.b200w_upload_pcm.argtypes = [vp, _c_float_p, cl, _c_int_p, ci]
@@ -108,9 +109,18 @@ def load_library():
     lib.b200w_test_parse_config.argtypes = [cp, cp, ctypes.POINTER(Dims), _c_int_p]
     lib.b200w_test_load_wav.argtypes = [cp, _c_float_p, ci, _c_int_p, _c_int_p, _c_int_p]
     lib.b200w_test_base64.argtypes = [cp, ctypes.c_char_p, ci]
-    lib.b200w_test_detokenize.argtypes = [cp, _c_int_p, ci, ctypes.c_char_p, ci]
+    _sig(lib, "b200w_test_detokenize", [cp, _c_int_p, ci, ctypes.c_char_p, ci])
     _lib = lib
     return lib
+
+
+def _sig(lib, name, argtypes):
+    """argtypes of an entry point added after round 1; an older A/B build (B200W_LIB) may lack it."""
+    try:
+        getattr(lib, name).argtypes = argtypes
+    except AttributeError:
+        if not os.environ.get("B200W_LIB"):
+            raise
 
 
 def _fp(a):
@@ -267,6 +277,12 @@ class Engine:
         self._check(self.lib.b200w_greedy(self.h, batch, language.encode(), max_new_tokens, int(honor_eot), _ip(forced), flen,
                                           _fp(logits), _ip(toks), N_TEXT_CTX, _ip(n)))
         return [toks[b, : n[b]].tolist() for b in range(batch)], logits
+
+    def decode_stats(self):
+        """(EOT compactions of the slot list since creation, sequences still decoding when the last greedy loop stopped)."""
+        c, a = ctypes.c_long(), ctypes.c_int()
+        self._check(self.lib.b200w_decode_stats(self.h, ctypes.byref(c), ctypes.byref(a)))
+        return c.value, a.value
 
     def transcribe(self, audios, language="zh", max_new_tokens=0, honor_eot=True):
         pcm, n = self._pack_pcm(audios)

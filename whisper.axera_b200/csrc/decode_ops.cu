@@ -65,13 +65,13 @@ __device__ __forceinline__ void axpy8(float (&acc)[8], float p, const uint4& v) 
 constexpr float kScoreScaleLog2 = 0.125f * 1.4426950408889634f;  // (64^-0.25)^2 * log2(e)
 
 // ---- embedding -------------------------------------------------------------------------------------------
-__global__ void embed_kernel(const int* __restrict__ step_ptr, const int* __restrict__ tokens, const float* __restrict__ tok_emb,
-                             const float* __restrict__ pos_emb, float* __restrict__ x, int d, int n_text_ctx) {
+__global__ void embed_kernel(const int* __restrict__ step_ptr, const int* __restrict__ tokens, const int* __restrict__ slot_seq,
+                             const float* __restrict__ tok_emb, const float* __restrict__ pos_emb, float* __restrict__ x, int d, int n_text_ctx) {
   pdl_wait();
   pdl_launch_dependents();
-  const int b = blockIdx.x;
+  const int b = blockIdx.x;  // slot
   const int step = *step_ptr;
-  const int tok = tokens[(long)b * n_text_ctx + step];
+  const int tok = tokens[(long)slot_seq[b] * n_text_ctx + step];
   const float4* te = reinterpret_cast<const float4*>(tok_emb + (long)tok * d);
   const float4* pe = reinterpret_cast<const float4*>(pos_emb + (long)step * d);
   float4* xo = reinterpret_cast<float4*>(x + (long)b * d);
@@ -89,7 +89,8 @@ __global__ void embed_kernel(const int* __restrict__ step_ptr, const int* __rest
 constexpr int kSelfWarps = 4;
 __global__ void __launch_bounds__(kSelfWarps * 32) self_attention_decode_kernel(const float* __restrict__ qkv, __nv_bfloat16* __restrict__ k_cache,
                                                                                __nv_bfloat16* __restrict__ v_cache, const int* __restrict__ step_ptr,
-                                                                               __nv_bfloat16* __restrict__ out, int n_pairs, int n_head, int n_ctx) {
+                                                                               const int* __restrict__ slot_seq, __nv_bfloat16* __restrict__ out,
+                                                                               int n_pairs, int n_head, int n_ctx) {
   pdl_wait();
   pdl_launch_dependents();
   const int pair = blockIdx.x * kSelfWarps + (threadIdx.x >> 5);  // b * n_head + h
@@ -99,8 +100,9 @@ __global__ void __launch_bounds__(kSelfWarps * 32) self_attention_decode_kernel(
   const int d = n_head * 64;
   const int pos = *step_ptr;  // cached positions 0..pos-1, current token at pos
   const float* qg = qkv + (long)b * 3 * d + h * 64 + sub * 8;
-  __nv_bfloat16* Kc = k_cache + (long)pair * n_ctx * 64;
-  __nv_bfloat16* Vc = v_cache + (long)pair * n_ctx * 64;
+  const long cpair = (long)slot_seq[b] * n_head + h;  // the cache belongs to the sequence, the activations to the slot
+  __nv_bfloat16* Kc = k_cache + cpair * n_ctx * 64;
+  __nv_bfloat16* Vc = v_cache + cpair * n_ctx * 64;
   float q[8], k1[8], v1[8];
   {
     const float4 a = *reinterpret_cast<const float4*>(qg), c = *reinterpret_cast<const float4*>(qg + 4);
@@ -203,7 +205,7 @@ constexpr int kXMaxSegPerCta = 3;                              // split kernel: 
 // Small batches: cluster of n_split CTAs per (sequence, head), n_split dividing the segment count.
 __global__ void __launch_bounds__(kCrossThreads)
 cross_attention_split_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
-                             __nv_bfloat16* __restrict__ out, int T, int evict_first) {
+                             const int* __restrict__ slot_seq, __nv_bfloat16* __restrict__ out, int T, int n_head, int evict_first) {
   constexpr int NW = kCrossThreads / 32;
   __shared__ float s_scores[kXMaxSegPerCta * kXKeysPerStep];
   __shared__ __align__(16) float s_part[kXMaxSegPerCta][8][kCrossThreads];  // per-thread segment partials of p.v (read by rank 0)
@@ -217,11 +219,13 @@ cross_attention_split_kernel(const float* __restrict__ q, const __nv_bfloat16* _
   const uint32_t n_split = cluster_nctarank(), rank = cluster_ctarank();
   const int seg_per = nseg / (int)n_split;           // the launcher picks n_split dividing nseg
   const int seg0 = (int)rank * seg_per;
-  const int item = blockIdx.x / n_split;             // (sequence, head) in the cache's own order
+  const int item = blockIdx.x / n_split;             // (slot, head): q / out index
+  const int slot = item / n_head;
+  const long citem = (long)slot_seq[slot] * n_head + (item - slot * n_head);  // (sequence, head): cache index
   const int key0 = warp * 4 + grp;
   const uint64_t pol = l2_evict_first_policy(evict_first != 0);
-  const __nv_bfloat16* kb = k + (long)item * T * 64 + sub * 8;
-  const __nv_bfloat16* vb = v + (long)item * T * 64 + sub * 8;
+  const __nv_bfloat16* kb = k + citem * T * 64 + sub * 8;
+  const __nv_bfloat16* vb = v + citem * T * 64 + sub * 8;
 
   // K of the first segment is requested before the dependency wait: the cross K/V cache was written by the encoder long ago,
   // only q depends on the predecessor kernel
@@ -339,14 +343,14 @@ cross_attention_split_kernel(const float* __restrict__ q, const __nv_bfloat16* _
 // it immediately instead of queueing behind undispatched CTAs.
 __global__ void __maxnreg__(64)
 cross_attention_stream_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
-                              __nv_bfloat16* __restrict__ out, int T, int n_items, int* __restrict__ work /*[2]: next item, CTAs done*/,
-                              int evict_first) {
+                              const int* __restrict__ slot_seq, __nv_bfloat16* __restrict__ out, int T, int n_head, int n_items,
+                              int* __restrict__ work /*[2]: next item, CTAs done*/, int evict_first) {
   constexpr int NW = kCrossThreads / 32;
   __shared__ float s_scores[kXMaxT];
   __shared__ float s_acc[NW * 64];
   __shared__ float s_redm[NW], s_redl[NW];
   __shared__ float s_q[2][64];
-  __shared__ int s_item[2];
+  __shared__ int s_item[2], s_citem[2];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int grp = lane >> 3, sub = lane & 7;  // 4 keys per warp instruction, 8 lanes (16 B each) per key
   const int nk = (T + kXKeysPerStep - 1) / kXKeysPerStep;  // steps per phase
@@ -356,14 +360,25 @@ cross_attention_stream_kernel(const float* __restrict__ q, const __nv_bfloat16* 
   pdl_wait();
   // items ((sequence, head) pairs in the cache's own order) are handed out by an atomic counter: every SM keeps exactly
   // the CTAs it was given busy until the work runs out, whatever B * H is
-  if (tid == 0) s_item[0] = atomicAdd(&work[0], 1);
+  // items are (slot, head) pairs (q / out index); the cache is indexed by (sequence, head): resolved once per claim by the
+  // claiming thread and published next to the item (no dependent global load on the streaming path)
+  auto cache_item = [&](int it) {
+    if (it >= n_items) return 0;
+    const int slot = it / n_head;
+    return slot_seq[slot] * n_head + (it - slot * n_head);
+  };
+  if (tid == 0) {
+    s_item[0] = atomicAdd(&work[0], 1);
+    s_citem[0] = cache_item(s_item[0]);
+  }
   __syncthreads();
   int item = s_item[0];
+  int citem = s_citem[0];
   int par = 0;
 
   // slot u of step (item, st): tensor K for st < nk else V, key (st % nk) * 256 + 32 u + key0
-  auto step_ptr = [&](int it, int st) {
-    const __nv_bfloat16* base = (st < nk ? k : v) + (long)it * T * 64;
+  auto step_ptr = [&](int cit, int st) {
+    const __nv_bfloat16* base = (st < nk ? k : v) + (long)cit * T * 64;
     const int kb = (st < nk ? st : st - nk) * kXKeysPerStep + key0;
     return base + (long)kb * 64 + sub * 8;
   };
@@ -372,7 +387,7 @@ cross_attention_stream_kernel(const float* __restrict__ q, const __nv_bfloat16* 
   if (item < n_items) {
     uint4 kv[kXU];
     {
-      const __nv_bfloat16* p0 = step_ptr(item, 0);
+      const __nv_bfloat16* p0 = step_ptr(citem, 0);
       const int j0 = step_key(0);
 #pragma unroll
       for (int u = 0; u < kXU; ++u) kv[u] = (j0 + 32 * u < T) ? ld_stream16_ef(p0 + u * 32 * 64, pol) : make_uint4(0, 0, 0, 0);
@@ -387,7 +402,7 @@ cross_attention_stream_kernel(const float* __restrict__ q, const __nv_bfloat16* 
       // first V segment -- is requested slot by slot while the current one is consumed ----
       float mx = -INFINITY;
       for (int st = 0; st < nk; ++st) {
-        const __nv_bfloat16* np = step_ptr(item, st + 1);
+        const __nv_bfloat16* np = step_ptr(citem, st + 1);
         const int nj = step_key(st + 1);
         const int j0 = step_key(st);
 #pragma unroll
@@ -407,7 +422,10 @@ cross_attention_stream_kernel(const float* __restrict__ q, const __nv_bfloat16* 
       // phase boundary: block maximum (the first V loads are already in flight)
       mx = warp_max(mx);
       if (lane == 0) s_redm[warp] = mx;
-      if (tid == 0) s_item[par ^ 1] = atomicAdd(&work[0], 1);  // claim the next item while V streams
+      if (tid == 0) {  // claim the next item while V streams
+        s_item[par ^ 1] = atomicAdd(&work[0], 1);
+        s_citem[par ^ 1] = cache_item(s_item[par ^ 1]);
+      }
       __syncthreads();
       float m = s_redm[0];
 #pragma unroll
@@ -428,7 +446,7 @@ cross_attention_stream_kernel(const float* __restrict__ q, const __nv_bfloat16* 
       for (int st = nk; st < spi; ++st) {
         const bool same = st + 1 < spi;
         const bool has_next = same || next_item < n_items;
-        const __nv_bfloat16* np = has_next ? step_ptr(same ? item : next_item, same ? st + 1 : 0) : k;
+        const __nv_bfloat16* np = has_next ? step_ptr(same ? citem : s_citem[par ^ 1], same ? st + 1 : 0) : k;
         const int nj = has_next ? step_key(same ? st + 1 : 0) : T;  // T: every slot predicated off
         const int j0 = step_key(st);
         float seg[8];
@@ -475,6 +493,7 @@ cross_attention_stream_kernel(const float* __restrict__ q, const __nv_bfloat16* 
       if (next_item >= n_items) break;
       item = next_item;
       par ^= 1;
+      citem = s_citem[par];
     }
   }
   pdl_launch_dependents();
@@ -516,12 +535,13 @@ __global__ void __launch_bounds__(128) argmax_finalize_kernel(DecodeState st, co
     for (int w = 1; w < 4; ++w)
       if (s_v[w] > best || (s_v[w] == best && s_i[w] < bi)) best = s_v[w], bi = s_i[w];
     const int pos = *st.step;
-    st.out_tokens[(long)b * n_text_ctx + pos] = bi;
+    const long seq = st.slot_seq[b];
+    st.out_tokens[seq * n_text_ctx + pos] = bi;
     if (pos + 1 >= sot_len && pos + 1 < n_text_ctx) {
-      const int f = st.forced ? st.forced[(long)b * n_text_ctx + pos + 1] : -1;
-      st.tokens[(long)b * n_text_ctx + pos + 1] = f >= 0 ? f : bi;
+      const int f = st.forced ? st.forced[seq * n_text_ctx + pos + 1] : -1;
+      st.tokens[seq * n_text_ctx + pos + 1] = f >= 0 ? f : bi;
     }
-    if (honor_eot && pos >= sot_len - 1 && bi == eot) st.finished[b] = 1;
+    if (honor_eot && pos >= sot_len - 1 && bi == eot) st.finished[seq] = 1;
   }
 }
 
@@ -578,14 +598,14 @@ int& launch_priority() {
 
 void launch_embed(const DecodeState& st, const float* tok_emb, const float* pos_emb, float* x, int B, int d, int n_text_ctx,
                   cudaStream_t stream, bool pdl) {
-  launch_k(pdl, embed_kernel, dim3(B), dim3(128), 0, stream, st.step, st.tokens, tok_emb, pos_emb, x, d, n_text_ctx);
+  launch_k(pdl, embed_kernel, dim3(B), dim3(128), 0, stream, st.step, st.tokens, st.slot_seq, tok_emb, pos_emb, x, d, n_text_ctx);
 }
 
-void launch_self_attention_decode(const float* qkv, __nv_bfloat16* k_cache, __nv_bfloat16* v_cache, const int* step, __nv_bfloat16* out,
-                                  int B, int n_head, int n_ctx, cudaStream_t stream) {
+void launch_self_attention_decode(const float* qkv, __nv_bfloat16* k_cache, __nv_bfloat16* v_cache, const int* step, const int* slot_seq,
+                                  __nv_bfloat16* out, int B, int n_head, int n_ctx, cudaStream_t stream) {
   const int n_pairs = B * n_head;
   launch_pdl(self_attention_decode_kernel, dim3((n_pairs + kSelfWarps - 1) / kSelfWarps), dim3(kSelfWarps * 32), 0, stream, qkv, k_cache,
-             v_cache, step, out, n_pairs, n_head, n_ctx);
+             v_cache, step, slot_seq, out, n_pairs, n_head, n_ctx);
 }
 
 int cross_attention_pick_split(int B, int n_head, int T) {
@@ -609,8 +629,8 @@ int cross_attention_pick_split(int B, int n_head, int T) {
   return best;  // 0 only if no valid split exists (then the streaming kernel runs whatever the batch)
 }
 
-void launch_cross_attention_decode(const float* q, const __nv_bfloat16* k, const __nv_bfloat16* v, __nv_bfloat16* out, int B, int n_head,
-                                   int T, int n_split, cudaStream_t stream, bool pdl, int* work) {
+void launch_cross_attention_decode(const float* q, const __nv_bfloat16* k, const __nv_bfloat16* v, const int* slot_seq, __nv_bfloat16* out,
+                                   int B, int n_head, int T, int n_split, cudaStream_t stream, bool pdl, int* work) {
   const int n_items = B * n_head;
   static const int evict_first = getenv("B200W_NO_EVICT_FIRST") == nullptr;
   if (n_split <= 0) {
@@ -618,11 +638,11 @@ void launch_cross_attention_decode(const float* q, const __nv_bfloat16* k, const
     // single resident wave: three CTAs on every SM, items claimed dynamically
     static const int ctas_per_sm = getenv("B200W_CROSS_CTAS_PER_SM") ? atoi(getenv("B200W_CROSS_CTAS_PER_SM")) : 3;
     const int grid = std::min(n_items, ctas_per_sm * kNumSMs);
-    launch_k(pdl, cross_attention_stream_kernel, dim3(grid), dim3(kCrossThreads), 0, stream, q, k, v, out, T, n_items, work, evict_first);
+    launch_k(pdl, cross_attention_stream_kernel, dim3(grid), dim3(kCrossThreads), 0, stream, q, k, v, slot_seq, out, T, n_head, n_items, work, evict_first);
     return;
   }
-  launch_kc(pdl, n_split, cross_attention_split_kernel, dim3(n_items * n_split), dim3(kCrossThreads), 0, stream, q, k, v, out, T,
-            n_split == 1 ? 0 : evict_first);
+  launch_kc(pdl, n_split, cross_attention_split_kernel, dim3(n_items * n_split), dim3(kCrossThreads), 0, stream, q, k, v, slot_seq, out, T,
+            n_head, n_split == 1 ? 0 : evict_first);
 }
 
 void decode_ops_set_attributes() {}

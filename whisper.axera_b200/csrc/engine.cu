@@ -179,7 +179,8 @@ Engine::Engine(const std::string& model_root, const std::string& model_type, int
   cross_chain_forced_ = getenv("B200W_CROSS_CHAIN") != nullptr;
   if (const char* e = getenv("B200W_GRAPH_STEPS")) graph_steps_ = std::max(1, std::min(16, atoi(e)));
   for (auto& st : mb_streams_) CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-  CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&pinned_flags_), 4096 * sizeof(int)));
+  CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&pinned_flags_), 2 * kMaxPolled * sizeof(int)));
+  pinned_map_ = pinned_flags_ + kMaxPolled;
 
   const std::string dir = model_root + "/" + model_type;  // {root}/{type}/{type}-*  (Whisper.cpp:87-90)
   cfg_ = load_model_config(model_root, model_type);
@@ -379,7 +380,7 @@ void Engine::free_workspace() {
   // capacities that describe freed memory
   cap_ = 0, pcm_stride_ = 0, enc_sub_ = 0, dec_rows_pad_ = 0;
   pcm_ = mel_ = utt_max_ = x_enc_ = x_dec_ = qkv_dec_ = q_dec_ = logits_ = part_val_ = nullptr;
-  n_samples_ = part_idx_ = cross_work_ = step_ctr_ = nullptr;
+  n_samples_ = part_idx_ = cross_work_ = step_ctr_ = slot_seq_ = nullptr;
   mel_tm_ = conv1_out_ = h_enc_ = qkv_enc_ = attn_enc_ = mlp_enc_ = cross_k_ = cross_v_ = self_k_ = self_v_ = nullptr;
   h_dec_ = attn_dec_ = mlp_dec_ = nullptr;
   st_ = DecodeState{};
@@ -444,9 +445,11 @@ void Engine::allocate_workspace(int new_cap, long new_stride) {
   st_.tokens = dev_alloc<int>(o, (size_t)cap_ * kTextCtx);
   st_.forced = dev_alloc<int>(o, (size_t)cap_ * kTextCtx);
   st_.finished = dev_alloc<int>(o, cap_);
-  st_.n_generated = dev_alloc<int>(o, cap_);
   st_.out_tokens = dev_alloc<int>(o, (size_t)cap_ * kTextCtx);
-  st_.margins = nullptr;
+  slot_seq_ = dev_alloc<int>(o, cap_);
+  st_.slot_seq = slot_seq_;
+  slot_map_identity_ = false;
+  reset_slot_map();
   build_plans();
 }
 
@@ -501,14 +504,19 @@ void Engine::build_plans() {
   dec_plans_.resize(cfg_.l_dec);
   const char* bn_env = getenv("B200W_DEC_BN");
   const int bn = bn_env ? atoi(bn_env) : 32;  // N tile of the decoder-step GEMMs: narrow tiles = more CTAs streaming W (measured best)
+  // The three residual GEMMs of a decoder block also apply the LayerNorm that follows them (gemm_resid_ln.cu: one cluster per
+  // row block, statistics through distributed shared memory): 11 -> 8 dependent kernels per layer.  Needs d <= 1024.
+  fused_ln_ = gemm_resid_ln_supported(d);
+  const int bn_res = fused_ln_ ? 64 : bn;
+  const int epi_res = fused_ln_ ? EPI_RESID_LN_F32 : EPI_BIAS_RESID_F32;
   for (int i = 0; i < cfg_.l_dec; ++i) {
     const LayerDec& L = dec_[i];
     dec_plans_[i].qkv = keep(gemm_plan_create(flat(h_dec_, d, dec_rows_pad_), L.w_qkv, 3 * d, bn, EPI_BIAS_F32));
-    dec_plans_[i].out = keep(gemm_plan_create(flat(attn_dec_, d, dec_rows_pad_), L.w_out, d, bn, EPI_BIAS_RESID_F32));
+    dec_plans_[i].out = keep(gemm_plan_create(flat(attn_dec_, d, dec_rows_pad_), L.w_out, d, bn_res, epi_res));
     dec_plans_[i].cq = keep(gemm_plan_create(flat(h_dec_, d, dec_rows_pad_), L.w_cq, d, bn, EPI_BIAS_F32));
-    dec_plans_[i].co = keep(gemm_plan_create(flat(attn_dec_, d, dec_rows_pad_), L.w_co, d, bn, EPI_BIAS_RESID_F32));
+    dec_plans_[i].co = keep(gemm_plan_create(flat(attn_dec_, d, dec_rows_pad_), L.w_co, d, bn_res, epi_res));
     dec_plans_[i].fc1 = keep(gemm_plan_create(flat(h_dec_, d, dec_rows_pad_), L.w_fc1, 4 * d, bn, EPI_BIAS_GELU_BF16));
-    dec_plans_[i].fc2 = keep(gemm_plan_create(flat(mlp_dec_, 4 * d, dec_rows_pad_), L.w_fc2, d, bn, EPI_BIAS_RESID_F32));
+    dec_plans_[i].fc2 = keep(gemm_plan_create(flat(mlp_dec_, 4 * d, dec_rows_pad_), L.w_fc2, d, bn_res, epi_res));
   }
   p_logits_ = keep(gemm_plan_create(flat(h_dec_, d, dec_rows_pad_), w_emb_bf16_, vocab_pad_, 128, EPI_ARGMAX));
 }
@@ -620,6 +628,13 @@ void Engine::enqueue_decode_step(int B, bool want_logits, bool finalize, int hon
     q.use_pdl = 1, q.a_row_offset = m.b0;
     return q;
   };
+  // residual GEMM x += ...; with the fused epilogue it also writes h = LayerNorm(x) with the given parameters (else the caller
+  // launches the LayerNorm kernel)
+  auto gp_res = [&](const MB& m, const float* bias, const float* ln_g, const float* ln_b) {
+    GemmParams q = gp(m, x_dec_, 4, d, d, bias);
+    if (fused_ln_) q.ln_gamma = ln_g, q.ln_beta = ln_b, q.ln_out = h_dec_ + (size_t)m.b0 * d, q.ln_ldo = d;
+    return q;
+  };
   // n_fused consecutive steps in one enqueue (= one CUDA graph): every micro-batch has its own step counter and moves on to
   // its next step without waiting for the others, so one micro-batch's logits / arg-max / embedding run underneath the other's
   // cross attention instead of leaving HBM idle at every step boundary
@@ -627,7 +642,7 @@ void Engine::enqueue_decode_step(int B, bool want_logits, bool finalize, int hon
     for (int i = 0; i < n_mb; ++i) {
       DecodeState st = st_;
       st.step = step_ctr_ + i;
-      st.tokens += (size_t)mb[i].b0 * kTextCtx;
+      st.slot_seq = slot_seq_ + mb[i].b0;  // token tables and caches are per sequence, rows per slot
       launch_embed(st, emb_f32_, pos_text_, x_dec_ + (size_t)mb[i].b0 * d, mb[i].nb, d, kTextCtx, mb[i].s, /*pdl=*/n_mb == 1 || fs > 0);
     }
     launches_ += n_mb;
@@ -636,21 +651,21 @@ void Engine::enqueue_decode_step(int B, bool want_logits, bool finalize, int hon
       const DecPlans& P = dec_plans_[l];
       for (int i = 0; i < n_mb; ++i) {
         const MB& m = mb[i];
-        const size_t skv_off = ((size_t)l * cap_ + m.b0) * H * kTextCtx * 64;
+        const size_t skv_off = (size_t)l * cap_ * H * kTextCtx * 64;  // layer base; the kernel adds the sequence of each slot
         float* x = x_dec_ + (size_t)m.b0 * d;
         __nv_bfloat16* h = h_dec_ + (size_t)m.b0 * d;
-        launch_layernorm(x, L.ln1_g, L.ln1_b, h, m.nb, d, m.s);
+        if (!fused_ln_ || l == 0) launch_layernorm(x, L.ln1_g, L.ln1_b, h, m.nb, d, m.s);  // fused: the previous layer's fc2 wrote h
         gemm_launch(P.qkv, gp(m, qkv_dec_, 4, 3 * d, 3 * d, L.b_qkv), m.s);
-        launch_self_attention_decode(qkv_dec_ + (size_t)m.b0 * 3 * d, self_k_ + skv_off, self_v_ + skv_off, step_ctr_ + i,
+        launch_self_attention_decode(qkv_dec_ + (size_t)m.b0 * 3 * d, self_k_ + skv_off, self_v_ + skv_off, step_ctr_ + i, slot_seq_ + m.b0,
                                      attn_dec_ + (size_t)m.b0 * d, m.nb, H, kTextCtx, m.s);
-        gemm_launch(P.out, gp(m, x_dec_, 4, d, d, L.b_out), m.s);
-        launch_layernorm(x, L.lnx_g, L.lnx_b, h, m.nb, d, m.s);
+        gemm_launch(P.out, gp_res(m, L.b_out, L.lnx_g, L.lnx_b), m.s);
+        if (!fused_ln_) launch_layernorm(x, L.lnx_g, L.lnx_b, h, m.nb, d, m.s);
         gemm_launch(P.cq, gp(m, q_dec_, 4, d, d, L.b_cq), m.s);
       }
       for (int i = 0; i < n_mb; ++i) {
         const MB& m = mb[i];
         const int n_split = cross_attention_pick_split(m.nb, H, kAudioCtx);
-        const size_t ckv_off = ((size_t)l * cap_ + m.b0) * H * kAudioCtx * 64;
+        const size_t ckv_off = (size_t)l * cap_ * H * kAudioCtx * 64;
         if (chain) {
           // the cross-attention kernels take turns on HBM: micro-batch i waits for micro-batch i-1's kernel of this layer,
           // micro-batch 0 for the last micro-batch's kernel of the previous layer
@@ -659,8 +674,9 @@ void Engine::enqueue_decode_step(int B, bool want_logits, bool finalize, int hon
         }
         {
           ScopedLaunchPriority low(0);
-          launch_cross_attention_decode(q_dec_ + (size_t)m.b0 * d, cross_k_ + ckv_off, cross_v_ + ckv_off, attn_dec_ + (size_t)m.b0 * d,
-                                        m.nb, H, kAudioCtx, n_split, m.s, /*pdl=*/!chain, cross_work_ + (l * 4 + i) * 2);
+          launch_cross_attention_decode(q_dec_ + (size_t)m.b0 * d, cross_k_ + ckv_off, cross_v_ + ckv_off, slot_seq_ + m.b0,
+                                        attn_dec_ + (size_t)m.b0 * d, m.nb, H, kAudioCtx, n_split, m.s, /*pdl=*/!chain,
+                                        cross_work_ + (l * 4 + i) * 2);
         }
         if (chain) CUDA_CHECK(cudaEventRecord(cross_event(l, i), m.s));
         launches_ += 1;
@@ -669,26 +685,27 @@ void Engine::enqueue_decode_step(int B, bool want_logits, bool finalize, int hon
         const MB& m = mb[i];
         float* x = x_dec_ + (size_t)m.b0 * d;
         __nv_bfloat16* h = h_dec_ + (size_t)m.b0 * d;
-        gemm_launch(P.co, gp(m, x_dec_, 4, d, d, L.b_co), m.s);
-        launch_layernorm(x, L.ln2_g, L.ln2_b, h, m.nb, d, m.s);
+        gemm_launch(P.co, gp_res(m, L.b_co, L.ln2_g, L.ln2_b), m.s);
+        if (!fused_ln_) launch_layernorm(x, L.ln2_g, L.ln2_b, h, m.nb, d, m.s);
         gemm_launch(P.fc1, gp(m, mlp_dec_, 2, 4 * d, 4 * d, L.b_fc1), m.s);
-        gemm_launch(P.fc2, gp(m, x_dec_, 4, d, d, L.b_fc2), m.s);
+        // fc2 also produces the next consumer's input: LayerNorm 1 of the next block, or the decoder's final LayerNorm
+        const bool last = l + 1 == Ld;
+        gemm_launch(P.fc2, gp_res(m, L.b_fc2, last ? dec_ln_g_ : dec_[l + 1].ln1_g, last ? dec_ln_b_ : dec_[l + 1].ln1_b), m.s);
       }
-      launches_ += 10 * n_mb;
+      launches_ += (fused_ln_ ? 7 + (l == 0 ? 1 : 0) : 10) * n_mb;
     }
     for (int i = 0; i < n_mb; ++i) {
       const MB& m = mb[i];
-      launch_layernorm(x_dec_ + (size_t)m.b0 * d, dec_ln_g_, dec_ln_b_, h_dec_ + (size_t)m.b0 * d, m.nb, d, m.s);
+      if (!fused_ln_) launch_layernorm(x_dec_ + (size_t)m.b0 * d, dec_ln_g_, dec_ln_b_, h_dec_ + (size_t)m.b0 * d, m.nb, d, m.s);
       GemmParams p = gp(m, want_logits ? logits_ : nullptr, 4, vocab_pad_, cfg_.n_vocab, nullptr);
       if (!want_logits) p.out = nullptr;
       p.part_val = part_val_ + (size_t)m.b0 * logits_tiles_, p.part_idx = part_idx_ + (size_t)m.b0 * logits_tiles_, p.part_ld = logits_tiles_;
       gemm_launch(p_logits_, p, m.s);
-      launches_ += 2;
+      launches_ += fused_ln_ ? 1 : 2;
       if (finalize) {
         DecodeState st = st_;
         st.step = step_ctr_ + i;
-        st.tokens += (size_t)m.b0 * kTextCtx, st.forced += (size_t)m.b0 * kTextCtx, st.out_tokens += (size_t)m.b0 * kTextCtx;
-        st.finished += m.b0;
+        st.slot_seq = slot_seq_ + m.b0;
         launch_argmax_finalize(st, p.part_val, p.part_idx, logits_tiles_, logits_tiles_, m.nb, kTextCtx, cfg_.eot, honor_eot, kSotLen, m.s);
         launch_advance_step(step_ctr_ + i, m.s, /*pdl=*/true);  // this micro-batch's own step counter
         launches_ += 2;
@@ -707,7 +724,7 @@ void Engine::run_cross_attention_only(int B) {
   const int n_split = cross_attention_pick_split(B, H, kAudioCtx);
   for (int l = 0; l < cfg_.l_dec; ++l) {
     const size_t ckv_off = (size_t)l * cap_ * H * kAudioCtx * 64;
-    launch_cross_attention_decode(q_dec_, cross_k_ + ckv_off, cross_v_ + ckv_off, attn_dec_, B, H, kAudioCtx, n_split, stream_, true,
+    launch_cross_attention_decode(q_dec_, cross_k_ + ckv_off, cross_v_ + ckv_off, slot_seq_, attn_dec_, B, H, kAudioCtx, n_split, stream_, true,
                                   cross_work_ + (size_t)cfg_.l_dec * 4 * 2);
     launches_ += 1;
   }
@@ -725,6 +742,17 @@ void Engine::decode_reset(int B) {
   CUDA_CHECK(cudaMemsetAsync(step_ctr_, 0, 4 * sizeof(int), stream_));
   CUDA_CHECK(cudaMemsetAsync(st_.finished, 0, sizeof(int) * B, stream_));
   CUDA_CHECK(cudaMemsetAsync(st_.forced, 0xff, sizeof(int) * (size_t)B * kTextCtx, stream_));  // -1
+  reset_slot_map();
+}
+
+// slot i works on sequence i: the state outside run_decode's EOT compaction
+void Engine::reset_slot_map() {
+  if (slot_map_identity_) return;
+  std::vector<int> id(cap_);
+  for (int i = 0; i < cap_; ++i) id[i] = i;
+  CUDA_CHECK(cudaMemcpyAsync(slot_seq_, id.data(), sizeof(int) * cap_, cudaMemcpyHostToDevice, stream_));
+  CUDA_CHECK(cudaStreamSynchronize(stream_));  // `id` is a stack-owned host vector
+  slot_map_identity_ = true;
 }
 
 int Engine::run_decode(int B, const std::vector<int>& sot, const DecodeOptions& opt, std::vector<std::vector<int>>* tokens) {
@@ -752,7 +780,7 @@ int Engine::run_decode(int B, const std::vector<int>& sot, const DecodeOptions& 
   const bool want_logits = opt.logits_out != nullptr;
   const bool graph = opt.use_graph && !want_logits && getenv("B200W_NO_GRAPH") == nullptr;
   // graphs of `k` consecutive decoder steps (k = graph_steps_ and, for the remainder, 1), cached per (B, honor_eot, k)
-  auto get_graph = [&](int k) {
+  auto get_graph = [&](int B, int k) {  // B = number of active slots
     const int key = (B * 2 + (opt.honor_eot ? 1 : 0)) * 64 + k;
     auto it = graphs_.find(key);
     if (it != graphs_.end()) return std::make_pair(it->second, per_step_launches_[key]);
@@ -786,16 +814,20 @@ int Engine::run_decode(int B, const std::vector<int>& sot, const DecodeOptions& 
     return std::make_pair(exec, per_step_launches_[key]);
   };
   int steps_done = 0;
+  std::vector<int> active(B);  // sequences still decoding, in slot order
+  for (int b = 0; b < B; ++b) active[b] = b;
+  static const bool compact = getenv("B200W_NO_COMPACT") == nullptr;
   while (steps_done < n_steps) {
     int k = 1;
+    const int Ba = (int)active.size();
     if (graph) {
       k = (n_steps - steps_done >= graph_steps_) ? graph_steps_ : 1;
-      const auto ge = get_graph(k);
+      const auto ge = get_graph(Ba, k);
       CUDA_CHECK(cudaGraphLaunch(ge.first, stream_));
       launches_ += ge.second;
     } else {
       const int s = steps_done;
-      enqueue_decode_step(B, want_logits, true, opt.honor_eot ? 1 : 0);
+      enqueue_decode_step(Ba, want_logits, true, opt.honor_eot ? 1 : 0);
       if (want_logits && s >= kSotLen - 1 && s - (kSotLen - 1) < max_new) {
         // logits after consuming position s = prediction of generated token (s - 3)
         const size_t step_i = (size_t)(s - (kSotLen - 1));
@@ -810,14 +842,35 @@ int Engine::run_decode(int B, const std::vector<int>& sot, const DecodeOptions& 
       }
     }
     steps_done += k;
-    if (opt.honor_eot && (steps_done % 16 == 0) && steps_done < n_steps) {
-      CUDA_CHECK(cudaMemcpyAsync(pinned_flags_, st_.finished, sizeof(int) * std::min(B, 4096), cudaMemcpyDeviceToHost, stream_));
+    if (opt.honor_eot && (steps_done % 16 == 0) && steps_done < n_steps && B <= kMaxPolled) {
+      // EOT bookkeeping every 16 steps: stop when every sequence has finished; otherwise drop the finished ones from the slot
+      // list so that the remaining steps cost what the still-running sequences cost (nothing moves in HBM: caches and token
+      // tables are per sequence, kernels reach them through slot_seq).  Results do not change: a sequence's arithmetic is
+      // independent of the batch it runs in (decode_ops.cu).
+      CUDA_CHECK(cudaMemcpyAsync(pinned_flags_, st_.finished, sizeof(int) * B, cudaMemcpyDeviceToHost, stream_));
       CUDA_CHECK(cudaStreamSynchronize(stream_));
-      bool all = B <= 4096;
-      for (int b = 0; b < std::min(B, 4096) && all; ++b) all = pinned_flags_[b] != 0;
-      if (all) break;
+      std::vector<int> still;
+      still.reserve(active.size());
+      for (int s : active)
+        if (pinned_flags_[s] == 0) still.push_back(s);
+      if (still.empty()) break;
+      if (compact && !want_logits && (int)still.size() <= (int)active.size() - std::max(1, (int)active.size() / 8)) {
+        for (size_t i = 0; i < still.size(); ++i) pinned_map_[i] = still[i];
+        CUDA_CHECK(cudaMemcpyAsync(slot_seq_, pinned_map_, sizeof(int) * still.size(), cudaMemcpyHostToDevice, stream_));
+        slot_map_identity_ = false;
+        active.swap(still);
+        ++compactions_;
+        if (graphs_.size() > 48) {  // many distinct batch sizes over time: start the graph cache over
+          CUDA_CHECK(cudaStreamSynchronize(stream_));
+          for (auto& kv : graphs_) cudaGraphExecDestroy(kv.second);
+          graphs_.clear();
+          per_step_launches_.clear();
+        }
+      }
     }
   }
+  last_active_ = (int)active.size();
+  reset_slot_map();  // later stateful calls (decoder_loop, a new decode) see slot i == sequence i again
   if (tokens) {
     std::vector<int> out((size_t)B * kTextCtx);
     CUDA_CHECK(cudaMemcpyAsync(out.data(), st_.out_tokens, out.size() * sizeof(int), cudaMemcpyDeviceToHost, stream_));

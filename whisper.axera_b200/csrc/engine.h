@@ -118,6 +118,8 @@ class Engine {
   void run_cross_attention_only(int B);
 
   long launches() const { return launches_; }
+  long compactions() const { return compactions_; }   // EOT compactions of the slot list so far
+  int last_active() const { return last_active_; }    // sequences still decoding when the last run_decode stopped
 
  private:
   struct LayerEnc;
@@ -125,6 +127,7 @@ class Engine {
   void load_weights(const std::string& dir, const std::string& type);
   void free_workspace();
   void check_batch(int B, const char* what) const;
+  void reset_slot_map();
   void export_cache(const __nv_bfloat16* cache, int T, int b0, int nb, int n_rows, float* out) const;
   void import_cache(__nv_bfloat16* cache, int T, int B, int n_rows, const float* in);
   void allocate_workspace(int new_cap, long new_stride);
@@ -142,6 +145,7 @@ class Engine {
   std::vector<cudaEvent_t> step_events_;    // fork / join / per-layer cross-attention hand-over
   std::vector<cudaEvent_t> copy_events_;    // per encoder sub-batch: its PCM has been copied (pipelined transcribe())
   bool micro_batch_ = true;
+  bool fused_ln_ = false;                   // residual GEMMs of the decoder step apply the following LayerNorm (gemm_resid_ln.cu)
   int n_micro_batch_ = 2;                   // micro-batches of a decoder step (B200W_N_MICROBATCH, 1..4)
   bool cross_chain_forced_ = false;         // B200W_CROSS_CHAIN: hand over regardless of the launch size
   bool cross_chain_ = true;                 // hand the cross-attention kernels over micro-batch to micro-batch with events
@@ -191,7 +195,13 @@ class Engine {
   // decode graph cache (keyed by batch size)
   std::map<int, cudaGraphExec_t> graphs_;
   std::map<int, long> per_step_launches_;
-  int* pinned_flags_ = nullptr;
+  static constexpr int kMaxPolled = 4096;   // EOT polling / compaction covers batches up to this size
+  int* pinned_flags_ = nullptr;             // [kMaxPolled] finished flags, [kMaxPolled] new slot map (pinned host)
+  int* pinned_map_ = nullptr;
+  int* slot_seq_ = nullptr;                 // device [cap]: sequence of each decoder slot
+  bool slot_map_identity_ = false;
+  long compactions_ = 0;
+  int last_active_ = 0;
 };
 
 }  // namespace b200w

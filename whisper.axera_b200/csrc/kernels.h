@@ -43,6 +43,9 @@ enum GemmEpilogue : int {
   EPI_GELU_POS_F32 = 4,    // out f32  = gelu(acc + bias) + pos[row_in_batch][n]   (conv2 + positional embedding)
   EPI_CROSSKV_BF16 = 5,    // head-major bf16 scatter of the stacked cross-attention K/V projections
   EPI_ARGMAX = 6,          // per-row (max, first index) over this tile's columns -> partials (+ optional f32 logits)
+  EPI_RESID_LN_F32 = 7,    // out f32 += acc + bias, then ln_out bf16 = LayerNorm(out row) * gamma + beta: the residual update and the
+                           // LayerNorm that follows it in one kernel.  One thread-block cluster = all N tiles of a row block; the row
+                           // statistics are exchanged through distributed shared memory (decoder-step GEMMs, N = d <= 1024).
 };
 
 struct GemmOperandA {  // activation operand, viewed as [n_batch][rows][K] with arbitrary (16 B-multiple) pitches
@@ -78,6 +81,11 @@ struct GemmParams {
   __nv_bfloat16* cross_k;  // [L][B][H][T][64]
   __nv_bfloat16* cross_v;
   int d_model, n_head, n_ctx_kv, kv_batch, kv_batch_offset;
+  // EPI_RESID_LN_F32: LayerNorm applied to the updated residual rows (eps 1e-5), written as bf16 [rows][N] with pitch ln_ldo
+  const float* ln_gamma;
+  const float* ln_beta;
+  __nv_bfloat16* ln_out;
+  long ln_ldo;
   // EPI_ARGMAX
   float* part_val;       // [rows][n_tiles]
   int* part_idx;
@@ -98,6 +106,9 @@ GemmPlan* gemm_plan_create(const GemmOperandA& a, const __nv_bfloat16* w, int n_
                            const GemmTmaOut* out = nullptr);
 void gemm_plan_destroy(GemmPlan*);
 void gemm_launch(const GemmPlan* plan, const GemmParams& p, cudaStream_t stream);
+// whether the fused residual + LayerNorm epilogue (EPI_RESID_LN_F32) can run for this width: needs d / 64 <= 16 CTAs per cluster
+// and a device that can co-schedule such a cluster
+bool gemm_resid_ln_supported(int d);
 // plain SIMT comparator used by the self-tests only (same operand conventions, f32 output = acc + bias)
 void gemm_reference_simt(const __nv_bfloat16* a, long lda, const __nv_bfloat16* w, long ldw, const float* bias, float* out,
                          long ldo, int M, int N, int K, cudaStream_t stream);
@@ -120,22 +131,24 @@ struct DecodeState {
   int* tokens;        // [B][n_text_ctx] token fed at each position (SOT prefix + generated)
   int* forced;        // [B][n_text_ctx] teacher-forcing tokens or -1
   int* finished;      // [B] 1 once EOT was produced (honoured only when honor_eot)
-  int* n_generated;   // [B]
   int* out_tokens;    // [B][n_text_ctx] generated tokens (argmax results)
-  float* margins;     // [B][n_text_ctx] top-1 logit value per step (diagnostics) or null
+  // Decoder rows ("slots") are decoupled from sequences: slot i of the step works on sequence slot_seq[i].  Activations are
+  // per slot, everything that persists across steps (token tables, finished flags, self / cross K/V caches) is per sequence,
+  // so dropping finished sequences (EOT) is just a shorter slot list -- nothing is moved in HBM.
+  const int* slot_seq;  // [n_slots]
 };
 // x[b] = tok_emb[token[b][step]] + pos_emb[step]      (f32)
 void launch_embed(const DecodeState& st, const float* tok_emb, const float* pos_emb, float* x, int B, int d, int n_text_ctx,
                   cudaStream_t stream, bool pdl = true);
-// self attention for one new token per sequence over a bf16 head-major cache [B][H][n_ctx][64];
+// self attention for one new token per slot over a bf16 head-major cache [n_seq][H][n_ctx][64] (sequence = slot_seq[slot]);
 // qkv f32 [B][3d] (q | k | v of the current token). Appends k,v at position *step, writes out bf16 [B][d].
-void launch_self_attention_decode(const float* qkv, __nv_bfloat16* k_cache, __nv_bfloat16* v_cache, const int* step,
+void launch_self_attention_decode(const float* qkv, __nv_bfloat16* k_cache, __nv_bfloat16* v_cache, const int* step, const int* slot_seq,
                                   __nv_bfloat16* out, int B, int n_head, int n_ctx, cudaStream_t stream);
-// cross attention: q f32 [B][d] over bf16 head-major K/V [B][H][T][64]; out bf16 [B][d].
+// cross attention: q f32 [B][d] (per slot) over bf16 head-major K/V [n_seq][H][T][64] (sequence = slot_seq[slot]); out bf16 [B][d].
 // n_split from cross_attention_pick_split(): 0 = streaming kernel (needs `work`: two zero-initialised ints owned by this launch
 // site), n > 0 = thread-block cluster of n CTAs per (sequence, head).  Every variant computes bit-identical results.
-void launch_cross_attention_decode(const float* q, const __nv_bfloat16* k, const __nv_bfloat16* v, __nv_bfloat16* out, int B,
-                                   int n_head, int T, int n_split, cudaStream_t stream, bool pdl = true, int* work = nullptr);
+void launch_cross_attention_decode(const float* q, const __nv_bfloat16* k, const __nv_bfloat16* v, const int* slot_seq, __nv_bfloat16* out,
+                                   int B, int n_head, int T, int n_split, cudaStream_t stream, bool pdl = true, int* work = nullptr);
 // reduces the argmax partials, applies teacher forcing / EOT bookkeeping, stores the next token
 void launch_advance_step(int* step, cudaStream_t stream, bool pdl = true);  // *step += 1 (once per decoder step)
 void launch_argmax_finalize(const DecodeState& st, const float* part_val, const int* part_idx, int n_tiles, int part_ld, int B,

@@ -208,6 +208,13 @@ int b200w_decoder_step(b200w_engine* e, const int* tokens, const float* self_k, 
   });
 }
 
+int b200w_decode_stats(const b200w_engine* e, long* compactions, int* last_active) {
+  if (!e) return -1;
+  if (compactions) *compactions = e->eng->compactions();
+  if (last_active) *last_active = e->eng->last_active();
+  return 0;
+}
+
 int b200w_set_logit_rows(b200w_engine* e, const int* rows, int n) {
   if (!e || n < 0 || (n > 0 && !rows)) return -1;
   e->logit_rows.assign(rows, rows + n);
@@ -410,7 +417,13 @@ int b200w_selftest_cross_attention(int B, int n_head, int T, unsigned seed, floa
     for (size_t i = 0; i < n_q; ++i) hq[i] = nd(rng) * 1.5f;
     __nv_bfloat16 *dk, *dv, *o;
     float* dq;
-    int* work;
+    int *work, *dmap;
+    // slot -> sequence map of the decoder (EOT compaction): a reversal here, so that q / out (per slot) and K / V (per
+    // sequence) are really indexed differently
+    std::vector<int> hmap(B);
+    for (int i = 0; i < B; ++i) hmap[i] = B - 1 - i;
+    CUDA_CHECK(cudaMalloc(&dmap, B * sizeof(int)));
+    CUDA_CHECK(cudaMemcpy(dmap, hmap.data(), B * sizeof(int), cudaMemcpyHostToDevice));
     CUDA_CHECK(cudaMalloc(&dk, n_kv * 2));
     CUDA_CHECK(cudaMalloc(&dv, n_kv * 2));
     CUDA_CHECK(cudaMalloc(&dq, n_q * 4));
@@ -429,12 +442,13 @@ int b200w_selftest_cross_attention(int B, int n_head, int T, unsigned seed, floa
     ref_items.push_back(n_items - 1);
     std::vector<std::vector<double>> ref(ref_items.size(), std::vector<double>(64));
     for (size_t r = 0; r < ref_items.size(); ++r) {
-      const int it = ref_items[r];
+      const int it = ref_items[r];                                               // (slot, head): q / out index
+      const size_t cit = (size_t)hmap[it / n_head] * n_head + (it % n_head);     // (sequence, head): cache index
       std::vector<double> sc(T);
       double mx = -1e300;
       for (int t = 0; t < T; ++t) {
         double a = 0;
-        for (int i = 0; i < 64; ++i) a += (double)hq[(size_t)it * 64 + i] * (double)__bfloat162float(hk[((size_t)it * T + t) * 64 + i]);
+        for (int i = 0; i < 64; ++i) a += (double)hq[(size_t)it * 64 + i] * (double)__bfloat162float(hk[(cit * T + t) * 64 + i]);
         sc[t] = a * 0.125;
         mx = std::max(mx, sc[t]);
       }
@@ -442,7 +456,7 @@ int b200w_selftest_cross_attention(int B, int n_head, int T, unsigned seed, floa
       for (int t = 0; t < T; ++t) {
         const double p = std::exp(sc[t] - mx);
         l += p;
-        for (int i = 0; i < 64; ++i) ref[r][i] += p * (double)__bfloat162float(hv[((size_t)it * T + t) * 64 + i]);
+        for (int i = 0; i < 64; ++i) ref[r][i] += p * (double)__bfloat162float(hv[(cit * T + t) * 64 + i]);
       }
       for (int i = 0; i < 64; ++i) ref[r][i] /= l;
     }
@@ -452,7 +466,7 @@ int b200w_selftest_cross_attention(int B, int n_head, int T, unsigned seed, floa
       if (n_split > 0 && (nseg % n_split != 0 || nseg / n_split > 3)) continue;
       CUDA_CHECK(cudaMemsetAsync(o, 0xff, n_q * 2, s));
       for (int rep = 0; rep < (n_split == 0 ? 2 : 1); ++rep)  // streaming kernel twice: the second launch runs on re-armed counters
-        launch_cross_attention_decode(dq, dk, dv, o, B, n_head, T, n_split, s, false, work);
+        launch_cross_attention_decode(dq, dk, dv, dmap, o, B, n_head, T, n_split, s, false, work);
       CUDA_CHECK(cudaStreamSynchronize(s));
       results.emplace_back(n_q);
       CUDA_CHECK(cudaMemcpy(results.back().data(), o, n_q * 2, cudaMemcpyDeviceToHost));
@@ -472,7 +486,7 @@ int b200w_selftest_cross_attention(int B, int n_head, int T, unsigned seed, floa
     *max_abs_diff = (float)md;
     *max_abs_ref_err = (float)me;
     cudaStreamDestroy(s);
-    cudaFree(dk), cudaFree(dv), cudaFree(dq), cudaFree(o), cudaFree(work);
+    cudaFree(dk), cudaFree(dv), cudaFree(dq), cudaFree(o), cudaFree(work), cudaFree(dmap);
   });
 }
 
@@ -523,6 +537,21 @@ int b200w_selftest_gemm(int M, int N, int K, int block_n, int epilogue, unsigned
     GemmPlan* plan = gemm_plan_create(a, dw, Npad, two_cta ? 256 : block_n, epilogue, two_cta);
     GemmParams p{};
     p.rows_valid = M, p.N = N, p.ldo = N, p.bias = db, p.n_batch = 1;
+    // fused residual + LayerNorm epilogue: random gamma / beta, bf16 LayerNorm output next to the updated f32 rows
+    std::vector<float> hg(N), hbeta(N);
+    for (int n = 0; n < N; ++n) hg[n] = 1.f + 0.1f * nd(rng), hbeta[n] = 0.1f * nd(rng);
+    float *dg = nullptr, *dbeta = nullptr;
+    __nv_bfloat16* dln = nullptr;
+    if (epilogue == EPI_RESID_LN_F32) {
+      if (!gemm_resid_ln_supported(N)) throw std::runtime_error("unsupported: this device cannot co-schedule the cluster the fused LayerNorm epilogue needs");
+      CUDA_CHECK(cudaMalloc(&dg, N * 4));
+      CUDA_CHECK(cudaMalloc(&dbeta, N * 4));
+      CUDA_CHECK(cudaMalloc(&dln, (size_t)M * N * 2));
+      CUDA_CHECK(cudaMemcpy(dg, hg.data(), N * 4, cudaMemcpyHostToDevice));
+      CUDA_CHECK(cudaMemcpy(dbeta, hbeta.data(), N * 4, cudaMemcpyHostToDevice));
+      CUDA_CHECK(cudaMemset(dln, 0xff, (size_t)M * N * 2));
+      p.ln_gamma = dg, p.ln_beta = dbeta, p.ln_out = dln, p.ln_ldo = N;
+    }
     const bool bf_out = epilogue == EPI_BIAS_BF16 || epilogue == EPI_BIAS_GELU_BF16;
     p.out = bf_out ? (void*)dout_bf : (void*)dout;
     p.part_val = dpv, p.part_idx = dpi, p.part_ld = n_tiles;
@@ -562,6 +591,29 @@ int b200w_selftest_gemm(int M, int N, int K, int block_n, int epilogue, unsigned
         }
         if (pbi != bi) md = std::max(md, 1e9);  // flag an argmax mismatch loudly
       }
+    } else if (epilogue == EPI_RESID_LN_F32) {
+      // host: x = resid + (A W^T + bias) [the SIMT comparator's f32 product], h = LayerNorm(x) * gamma + beta in fp64
+      std::vector<__nv_bfloat16> hl((size_t)M * N);
+      CUDA_CHECK(cudaMemcpy(hl.data(), dln, hl.size() * 2, cudaMemcpyDeviceToHost));
+      for (int m = 0; m < M; ++m) {
+        double mean = 0, var = 0;
+        for (int n = 0; n < N; ++n) mean += (double)ref[(size_t)m * N + n] + hres[(size_t)m * N + n];
+        mean /= N;
+        for (int n = 0; n < N; ++n) {
+          const double x = (double)ref[(size_t)m * N + n] + hres[(size_t)m * N + n] - mean;
+          var += x * x;
+        }
+        const double rstd = 1.0 / sqrt(var / N + 1e-5);
+        for (int n = 0; n < N; ++n) {
+          const double x = (double)ref[(size_t)m * N + n] + hres[(size_t)m * N + n];
+          const double h = (x - mean) * rstd * hg[n] + hbeta[n];
+          const float gh = __bfloat162float(hl[(size_t)m * N + n]);
+          if (!(gh == gh)) md = 1e9;
+          md = std::max(md, fabs((double)got[(size_t)m * N + n] - x));  // the updated residual row
+          md = std::max(md, fabs((double)gh - h));                       // its LayerNorm (bf16)
+          mr = std::max(mr, fabs(h));
+        }
+      }
     } else {
       for (size_t i = 0; i < ref.size(); ++i) {
         float r = ref[i];
@@ -576,6 +628,7 @@ int b200w_selftest_gemm(int M, int N, int K, int block_n, int epilogue, unsigned
     gemm_plan_destroy(plan);
     cudaStreamDestroy(s);
     cudaFree(da), cudaFree(dw), cudaFree(db), cudaFree(dref), cudaFree(dout), cudaFree(dout_bf), cudaFree(dpv), cudaFree(dpi);
+    cudaFree(dg), cudaFree(dbeta), cudaFree(dln);
   });
 }
 
