@@ -1,4 +1,5 @@
-"""K4 tcgen05 GEMM (through the C ABI test hook) against the plain SIMT comparator on the same bf16 inputs."""
+"""K4 tcgen05 GEMM (through the C ABI test hook) against the plain SIMT comparator on the same bf16 inputs (every element) and
+against an fp64 host evaluation of sample rows (independent of any CUDA code)."""
 import pytest
 
 pytestmark = pytest.mark.gpu
@@ -24,25 +25,13 @@ CASES = [
     (3000, 384, 1536, 512, 3),
     (1000, 1536, 384, 512, 1),
     (48000, 768, 768, 512, 3),   # encoder-sized: many tile pairs per cluster
-    # epilogue 7 = residual update + the following LayerNorm in one cluster kernel (gemm_resid_ln.cu, 64-column tiles, N = d)
-    (128, 768, 768, 64, 7),      # small: out-projection, cluster of 12
-    (37, 768, 3072, 64, 7),      # small: fc2, ragged M
-    (128, 512, 512, 64, 7),      # base: cluster of 8
-    (16, 384, 1536, 64, 7),      # tiny
-    (200, 1024, 256, 64, 7),     # two row blocks, cluster of 16 (the largest)
-    (3, 128, 128, 64, 7),        # micro: cluster of 2
 ]
 
 
 @pytest.mark.parametrize("M,N,K,block_n,epi", CASES)
 def test_gemm_matches_simt(pkg, M, N, K, block_n, epi):
-    try:
-        diff, ref = pkg.selftest_gemm(M, N, K, block_n, epi, seed=M + N + K)
-    except pkg.B200Error as ex:
-        if "unsupported" in str(ex) and N // 64 > 12:  # a 16-CTA cluster is optional (no BASELINE architecture has d = 1024)
-            pytest.skip(str(ex))
-        raise
+    diff, ref = pkg.selftest_gemm(M, N, K, block_n, epi, seed=M + N + K)
     # fp32 accumulation on identical bf16 inputs: only summation order differs (bf16 outputs add 2^-9 relative)
-    tol = 2e-3 * max(ref, 1.0) if epi in (2, 3, 6) else 1.2e-2 * max(ref, 1.0)  # 7: the LayerNorm output is bf16 as well
+    tol = 2e-3 * max(ref, 1.0) if epi in (2, 3, 6) else 1.2e-2 * max(ref, 1.0)
     assert ref > 0.1, "comparator output is degenerate"
     assert diff <= tol, "tcgen05 GEMM differs from the SIMT comparator: max|diff| %g (max|ref| %g)" % (diff, ref)

@@ -8,7 +8,7 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompil
 OBJ=${OBJ:-obj}   # OBJ / OUT elsewhere = a scratch build that leaves the in-tree library untouched (e.g. while a gpurun call is queued)
 mkdir -p $OBJ
 pids=()
-for f in logmel.cu gemm_tcgen05.cu gemm2cta_tcgen05.cu gemm_resid_ln.cu encoder_ops.cu attention_tcgen05.cu decode_ops.cu engine.cu model_abi.cu; do
+for f in logmel.cu gemm_tcgen05.cu gemm2cta_tcgen05.cu encoder_ops.cu attention_tcgen05.cu decode_ops.cu engine.cu model_abi.cu; do
   if [ ! -f $OBJ/${f%.cu}.o ] || [ $f -nt $OBJ/${f%.cu}.o ] || [ -n "$(find . -maxdepth 1 \( -name '*.h' -o -name '*.cuh' -o -name '*.inc' \) -newer $OBJ/${f%.cu}.o)" ] || [ -n "$(find ../../include -name '*.h' -newer $OBJ/${f%.cu}.o)" ]; then
     $NVCC $FLAGS -c $f -o $OBJ/${f%.cu}.o &
     pids+=($!)

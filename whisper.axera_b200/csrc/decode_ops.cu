@@ -578,6 +578,123 @@ __global__ void kv_export_kernel(const __nv_bfloat16* __restrict__ src, float* _
   *reinterpret_cast<float4*>(o + 4) = make_float4(bf16lo_to_f32(u.z), bf16hi_to_f32(u.z), bf16lo_to_f32(u.w), bf16hi_to_f32(u.w));
 }
 
+// ---- step boundary: argmax finalize + loop bookkeeping + NEXT step's embedding + first LayerNorm + step counter ----------
+// One kernel instead of four dependent ones (argmax_finalize, advance_step, embed, layernorm): at mid-size batches the decoder
+// step is bound by its chain of short kernels, not by HBM.  One CTA per slot; the last CTA to finish advances the step counter
+// (every CTA has read it by then).
+constexpr int kBoundaryThreads = 128;
+constexpr int kBoundaryMaxVec = 3;  // float4 per thread: d <= 1536
+__global__ void __launch_bounds__(kBoundaryThreads)
+step_boundary_kernel(DecodeState st, const float* __restrict__ part_val, const int* __restrict__ part_idx, int n_tiles, int part_ld, int n_text_ctx,
+                     int eot, int honor_eot, int sot_len, const float* __restrict__ tok_emb, const float* __restrict__ pos_emb,
+                     const float* __restrict__ ln_g, const float* __restrict__ ln_b, float* __restrict__ x, __nv_bfloat16* __restrict__ h, int d,
+                     int* __restrict__ ticket) {
+  __shared__ float s_v[4];
+  __shared__ int s_i[4];
+  __shared__ int s_next[2];
+  __shared__ float s_red[4];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float best = -FLT_MAX;
+  int bi = 0x7fffffff;
+  for (int i = tid; i < n_tiles; i += kBoundaryThreads) {
+    const float v = part_val[(long)b * part_ld + i];
+    const int ix = part_idx[(long)b * part_ld + i];
+    if (v > best || (v == best && ix < bi)) best = v, bi = ix;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) best = ov, bi = oi;
+  }
+  if (lane == 0) s_v[warp] = best, s_i[warp] = bi;
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 4; ++w)
+      if (s_v[w] > best || (s_v[w] == best && s_i[w] < bi)) best = s_v[w], bi = s_i[w];
+    const int pos = *st.step;
+    const long seq = st.slot_seq[b];
+    st.out_tokens[seq * n_text_ctx + pos] = bi;
+    int next = -1;
+    if (pos + 1 < n_text_ctx) {
+      if (pos + 1 >= sot_len) {
+        const int f = st.forced ? st.forced[seq * n_text_ctx + pos + 1] : -1;
+        next = f >= 0 ? f : bi;
+        st.tokens[seq * n_text_ctx + pos + 1] = next;
+      } else {
+        next = st.tokens[seq * n_text_ctx + pos + 1];  // still inside the SOT prefix
+      }
+    }
+    if (honor_eot && pos >= sot_len - 1 && bi == eot) st.finished[seq] = 1;
+    s_next[0] = next;
+    s_next[1] = pos + 1;
+  }
+  __syncthreads();
+  const int tok = s_next[0], npos = s_next[1];
+  if (tok >= 0) {  // block-uniform
+    // x = token_embedding[tok] + positional_embedding[npos]; h = LayerNorm(x) (two-pass statistics like layernorm_kernel)
+    const int nvec = d >> 2;
+    const float4* te = reinterpret_cast<const float4*>(tok_emb + (long)tok * d);
+    const float4* pe = reinterpret_cast<const float4*>(pos_emb + (long)npos * d);
+    float4* xo = reinterpret_cast<float4*>(x + (long)b * d);
+    float4 v[kBoundaryMaxVec];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < kBoundaryMaxVec; ++k) {
+      const int i = tid + k * kBoundaryThreads;
+      if (i < nvec) {
+        const float4 a = te[i], p = pe[i];
+        v[k] = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
+        xo[i] = v[k];
+        s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+      }
+    }
+    s = warp_sum(s);
+    if (lane == 0) s_red[warp] = s;
+    __syncthreads();
+    const float mean = ((s_red[0] + s_red[1]) + (s_red[2] + s_red[3])) / (float)d;
+    __syncthreads();
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < kBoundaryMaxVec; ++k) {
+      const int i = tid + k * kBoundaryThreads;
+      if (i < nvec) {
+        const float a = v[k].x - mean, c = v[k].y - mean, e = v[k].z - mean, f = v[k].w - mean;
+        q += (a * a + c * c) + (e * e + f * f);
+      }
+    }
+    q = warp_sum(q);
+    if (lane == 0) s_red[warp] = q;
+    __syncthreads();
+    const float rstd = rsqrtf(((s_red[0] + s_red[1]) + (s_red[2] + s_red[3])) / (float)d + 1e-5f);
+    const float4* g4 = reinterpret_cast<const float4*>(ln_g);
+    const float4* b4 = reinterpret_cast<const float4*>(ln_b);
+    uint2* ho = reinterpret_cast<uint2*>(h + (long)b * d);
+#pragma unroll
+    for (int k = 0; k < kBoundaryMaxVec; ++k) {
+      const int i = tid + k * kBoundaryThreads;
+      if (i < nvec) {
+        const float4 g = g4[i], bb = b4[i];
+        uint2 o;
+        o.x = pack_bf16x2((v[k].x - mean) * rstd * g.x + bb.x, (v[k].y - mean) * rstd * g.y + bb.y);
+        o.y = pack_bf16x2((v[k].z - mean) * rstd * g.z + bb.z, (v[k].w - mean) * rstd * g.w + bb.w);
+        ho[i] = o;
+      }
+    }
+  }
+  // the last CTA advances the step counter: every CTA took its ticket after reading the counter
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(ticket, 1) == (int)gridDim.x - 1) {
+      *st.step = npos;
+      *ticket = 0;
+      __threadfence();
+    }
+  }
+}
+
 __global__ void advance_step_kernel(int* step) {
   pdl_wait();
   pdl_launch_dependents();
@@ -663,6 +780,14 @@ void launch_kv_export(const __nv_bfloat16* src, float* dst, int n_seq, int n_row
   if (total <= 0) return;
   kv_export_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(src, dst, n_seq, n_rows, T_src, T_dst, n_head);
   CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_step_boundary(const DecodeState& st, const float* part_val, const int* part_idx, int n_tiles, int part_ld, int B, int n_text_ctx,
+                          int eot, int honor_eot, int sot_len, const float* tok_emb, const float* pos_emb, const float* ln_g, const float* ln_b,
+                          float* x, __nv_bfloat16* h, int d, int* ticket, cudaStream_t stream) {
+  if (d % 4 != 0 || d / 4 > kBoundaryThreads * kBoundaryMaxVec) throw CudaError("step boundary: unsupported model width");
+  launch_pdl(step_boundary_kernel, dim3(B), dim3(kBoundaryThreads), 0, stream, st, part_val, part_idx, n_tiles, part_ld, n_text_ctx, eot, honor_eot,
+             sot_len, tok_emb, pos_emb, ln_g, ln_b, x, h, d, ticket);
 }
 
 void launch_advance_step(int* step, cudaStream_t stream, bool pdl) { launch_k(pdl, advance_step_kernel, dim3(1), dim3(1), 0, stream, step); }

@@ -380,7 +380,7 @@ void Engine::free_workspace() {
   // capacities that describe freed memory
   cap_ = 0, pcm_stride_ = 0, enc_sub_ = 0, dec_rows_pad_ = 0;
   pcm_ = mel_ = utt_max_ = x_enc_ = x_dec_ = qkv_dec_ = q_dec_ = logits_ = part_val_ = nullptr;
-  n_samples_ = part_idx_ = cross_work_ = step_ctr_ = slot_seq_ = nullptr;
+  n_samples_ = part_idx_ = cross_work_ = step_ctr_ = slot_seq_ = boundary_ticket_ = nullptr;
   mel_tm_ = conv1_out_ = h_enc_ = qkv_enc_ = attn_enc_ = mlp_enc_ = cross_k_ = cross_v_ = self_k_ = self_v_ = nullptr;
   h_dec_ = attn_dec_ = mlp_dec_ = nullptr;
   st_ = DecodeState{};
@@ -441,6 +441,7 @@ void Engine::allocate_workspace(int new_cap, long new_stride) {
   part_idx_ = dev_alloc<int>(o, (size_t)cap_ * logits_tiles_);
   cross_work_ = dev_alloc<int>(o, (size_t)cfg_.l_dec * 4 * 2 + 2);  // item counters of the streaming cross-attention launches
   step_ctr_ = dev_alloc<int>(o, 4);  // one step counter per micro-batch (they advance independently inside a graph)
+  boundary_ticket_ = dev_alloc<int>(o, 4);  // arrival counters of the step-boundary kernel, one per micro-batch
   st_.step = step_ctr_;
   st_.tokens = dev_alloc<int>(o, (size_t)cap_ * kTextCtx);
   st_.forced = dev_alloc<int>(o, (size_t)cap_ * kTextCtx);
@@ -504,19 +505,14 @@ void Engine::build_plans() {
   dec_plans_.resize(cfg_.l_dec);
   const char* bn_env = getenv("B200W_DEC_BN");
   const int bn = bn_env ? atoi(bn_env) : 32;  // N tile of the decoder-step GEMMs: narrow tiles = more CTAs streaming W (measured best)
-  // The three residual GEMMs of a decoder block also apply the LayerNorm that follows them (gemm_resid_ln.cu: one cluster per
-  // row block, statistics through distributed shared memory): 11 -> 8 dependent kernels per layer.  Needs d <= 1024.
-  fused_ln_ = gemm_resid_ln_supported(d);
-  const int bn_res = fused_ln_ ? 64 : bn;
-  const int epi_res = fused_ln_ ? EPI_RESID_LN_F32 : EPI_BIAS_RESID_F32;
   for (int i = 0; i < cfg_.l_dec; ++i) {
     const LayerDec& L = dec_[i];
     dec_plans_[i].qkv = keep(gemm_plan_create(flat(h_dec_, d, dec_rows_pad_), L.w_qkv, 3 * d, bn, EPI_BIAS_F32));
-    dec_plans_[i].out = keep(gemm_plan_create(flat(attn_dec_, d, dec_rows_pad_), L.w_out, d, bn_res, epi_res));
+    dec_plans_[i].out = keep(gemm_plan_create(flat(attn_dec_, d, dec_rows_pad_), L.w_out, d, bn, EPI_BIAS_RESID_F32));
     dec_plans_[i].cq = keep(gemm_plan_create(flat(h_dec_, d, dec_rows_pad_), L.w_cq, d, bn, EPI_BIAS_F32));
-    dec_plans_[i].co = keep(gemm_plan_create(flat(attn_dec_, d, dec_rows_pad_), L.w_co, d, bn_res, epi_res));
+    dec_plans_[i].co = keep(gemm_plan_create(flat(attn_dec_, d, dec_rows_pad_), L.w_co, d, bn, EPI_BIAS_RESID_F32));
     dec_plans_[i].fc1 = keep(gemm_plan_create(flat(h_dec_, d, dec_rows_pad_), L.w_fc1, 4 * d, bn, EPI_BIAS_GELU_BF16));
-    dec_plans_[i].fc2 = keep(gemm_plan_create(flat(mlp_dec_, 4 * d, dec_rows_pad_), L.w_fc2, d, bn_res, epi_res));
+    dec_plans_[i].fc2 = keep(gemm_plan_create(flat(mlp_dec_, 4 * d, dec_rows_pad_), L.w_fc2, d, bn, EPI_BIAS_RESID_F32));
   }
   p_logits_ = keep(gemm_plan_create(flat(h_dec_, d, dec_rows_pad_), w_emb_bf16_, vocab_pad_, 128, EPI_ARGMAX));
 }
@@ -592,7 +588,7 @@ void Engine::run_encoder_range(int b0, int nb) {
 // shared memory for others), the other runs its chain of short latency-bound kernels (LayerNorm, M <= 128 GEMMs, self
 // attention) on the same SMs.  Events hand the HBM "token" back and forth so the cross-attention kernels alternate instead
 // of competing; sequences are independent, so results do not change.
-void Engine::enqueue_decode_step(int B, bool want_logits, bool finalize, int honor_eot, int n_fused) {
+void Engine::enqueue_decode_step(int B, bool want_logits, bool finalize, int honor_eot, int n_fused, bool need_embed) {
   const int d = cfg_.d, H = cfg_.n_head, Ld = cfg_.l_dec;
   int n_mb = (micro_batch_ && B >= 32) ? n_micro_batch_ : 1;
   while (n_mb > 1 && B / n_mb < 16) --n_mb;
@@ -628,24 +624,24 @@ void Engine::enqueue_decode_step(int B, bool want_logits, bool finalize, int hon
     q.use_pdl = 1, q.a_row_offset = m.b0;
     return q;
   };
-  // residual GEMM x += ...; with the fused epilogue it also writes h = LayerNorm(x) with the given parameters (else the caller
-  // launches the LayerNorm kernel)
-  auto gp_res = [&](const MB& m, const float* bias, const float* ln_g, const float* ln_b) {
-    GemmParams q = gp(m, x_dec_, 4, d, d, bias);
-    if (fused_ln_) q.ln_gamma = ln_g, q.ln_beta = ln_b, q.ln_out = h_dec_ + (size_t)m.b0 * d, q.ln_ldo = d;
-    return q;
-  };
   // n_fused consecutive steps in one enqueue (= one CUDA graph): every micro-batch has its own step counter and moves on to
   // its next step without waiting for the others, so one micro-batch's logits / arg-max / embedding run underneath the other's
   // cross attention instead of leaving HBM idle at every step boundary
+  static const bool fuse_boundary = getenv("B200W_NO_STEP_BOUNDARY") == nullptr;
   for (int fs = 0; fs < n_fused; ++fs) {
-    for (int i = 0; i < n_mb; ++i) {
-      DecodeState st = st_;
-      st.step = step_ctr_ + i;
-      st.slot_seq = slot_seq_ + mb[i].b0;  // token tables and caches are per sequence, rows per slot
-      launch_embed(st, emb_f32_, pos_text_, x_dec_ + (size_t)mb[i].b0 * d, mb[i].nb, d, kTextCtx, mb[i].s, /*pdl=*/n_mb == 1 || fs > 0);
+    // x = embedding of the token at this position, h = LayerNorm 1 of the first block: produced by the previous step's boundary
+    // kernel, except for the first step of a decode (or after the slot list changed), where the caller asks for them here
+    const bool boundary_made_it = fuse_boundary && finalize && (fs > 0 || !need_embed);
+    if (!boundary_made_it) {
+      for (int i = 0; i < n_mb; ++i) {
+        DecodeState st = st_;
+        st.step = step_ctr_ + i;
+        st.slot_seq = slot_seq_ + mb[i].b0;  // token tables and caches are per sequence, rows per slot
+        launch_embed(st, emb_f32_, pos_text_, x_dec_ + (size_t)mb[i].b0 * d, mb[i].nb, d, kTextCtx, mb[i].s, /*pdl=*/n_mb == 1 || fs > 0);
+        launch_layernorm(x_dec_ + (size_t)mb[i].b0 * d, dec_[0].ln1_g, dec_[0].ln1_b, h_dec_ + (size_t)mb[i].b0 * d, mb[i].nb, d, mb[i].s);
+      }
+      launches_ += 2 * n_mb;
     }
-    launches_ += n_mb;
     for (int l = 0; l < Ld; ++l) {
       const LayerDec& L = dec_[l];
       const DecPlans& P = dec_plans_[l];
@@ -654,12 +650,12 @@ void Engine::enqueue_decode_step(int B, bool want_logits, bool finalize, int hon
         const size_t skv_off = (size_t)l * cap_ * H * kTextCtx * 64;  // layer base; the kernel adds the sequence of each slot
         float* x = x_dec_ + (size_t)m.b0 * d;
         __nv_bfloat16* h = h_dec_ + (size_t)m.b0 * d;
-        if (!fused_ln_ || l == 0) launch_layernorm(x, L.ln1_g, L.ln1_b, h, m.nb, d, m.s);  // fused: the previous layer's fc2 wrote h
+        if (l > 0) launch_layernorm(x, L.ln1_g, L.ln1_b, h, m.nb, d, m.s);  // l == 0: made by the embed / step-boundary kernel
         gemm_launch(P.qkv, gp(m, qkv_dec_, 4, 3 * d, 3 * d, L.b_qkv), m.s);
         launch_self_attention_decode(qkv_dec_ + (size_t)m.b0 * 3 * d, self_k_ + skv_off, self_v_ + skv_off, step_ctr_ + i, slot_seq_ + m.b0,
                                      attn_dec_ + (size_t)m.b0 * d, m.nb, H, kTextCtx, m.s);
-        gemm_launch(P.out, gp_res(m, L.b_out, L.lnx_g, L.lnx_b), m.s);
-        if (!fused_ln_) launch_layernorm(x, L.lnx_g, L.lnx_b, h, m.nb, d, m.s);
+        gemm_launch(P.out, gp(m, x_dec_, 4, d, d, L.b_out), m.s);
+        launch_layernorm(x, L.lnx_g, L.lnx_b, h, m.nb, d, m.s);
         gemm_launch(P.cq, gp(m, q_dec_, 4, d, d, L.b_cq), m.s);
       }
       for (int i = 0; i < n_mb; ++i) {
@@ -685,30 +681,35 @@ void Engine::enqueue_decode_step(int B, bool want_logits, bool finalize, int hon
         const MB& m = mb[i];
         float* x = x_dec_ + (size_t)m.b0 * d;
         __nv_bfloat16* h = h_dec_ + (size_t)m.b0 * d;
-        gemm_launch(P.co, gp_res(m, L.b_co, L.ln2_g, L.ln2_b), m.s);
-        if (!fused_ln_) launch_layernorm(x, L.ln2_g, L.ln2_b, h, m.nb, d, m.s);
+        gemm_launch(P.co, gp(m, x_dec_, 4, d, d, L.b_co), m.s);
+        launch_layernorm(x, L.ln2_g, L.ln2_b, h, m.nb, d, m.s);
         gemm_launch(P.fc1, gp(m, mlp_dec_, 2, 4 * d, 4 * d, L.b_fc1), m.s);
-        // fc2 also produces the next consumer's input: LayerNorm 1 of the next block, or the decoder's final LayerNorm
-        const bool last = l + 1 == Ld;
-        gemm_launch(P.fc2, gp_res(m, L.b_fc2, last ? dec_ln_g_ : dec_[l + 1].ln1_g, last ? dec_ln_b_ : dec_[l + 1].ln1_b), m.s);
+        gemm_launch(P.fc2, gp(m, x_dec_, 4, d, d, L.b_fc2), m.s);
       }
-      launches_ += (fused_ln_ ? 7 + (l == 0 ? 1 : 0) : 10) * n_mb;
+      launches_ += (l == 0 ? 9 : 10) * n_mb;
     }
     for (int i = 0; i < n_mb; ++i) {
       const MB& m = mb[i];
-      if (!fused_ln_) launch_layernorm(x_dec_ + (size_t)m.b0 * d, dec_ln_g_, dec_ln_b_, h_dec_ + (size_t)m.b0 * d, m.nb, d, m.s);
+      launch_layernorm(x_dec_ + (size_t)m.b0 * d, dec_ln_g_, dec_ln_b_, h_dec_ + (size_t)m.b0 * d, m.nb, d, m.s);
       GemmParams p = gp(m, want_logits ? logits_ : nullptr, 4, vocab_pad_, cfg_.n_vocab, nullptr);
       if (!want_logits) p.out = nullptr;
       p.part_val = part_val_ + (size_t)m.b0 * logits_tiles_, p.part_idx = part_idx_ + (size_t)m.b0 * logits_tiles_, p.part_ld = logits_tiles_;
       gemm_launch(p_logits_, p, m.s);
-      launches_ += fused_ln_ ? 1 : 2;
+      launches_ += 2;
       if (finalize) {
         DecodeState st = st_;
         st.step = step_ctr_ + i;
         st.slot_seq = slot_seq_ + m.b0;
-        launch_argmax_finalize(st, p.part_val, p.part_idx, logits_tiles_, logits_tiles_, m.nb, kTextCtx, cfg_.eot, honor_eot, kSotLen, m.s);
-        launch_advance_step(step_ctr_ + i, m.s, /*pdl=*/true);  // this micro-batch's own step counter
-        launches_ += 2;
+        if (fuse_boundary) {
+          launch_step_boundary(st, p.part_val, p.part_idx, logits_tiles_, logits_tiles_, m.nb, kTextCtx, cfg_.eot, honor_eot, kSotLen, emb_f32_,
+                               pos_text_, dec_[0].ln1_g, dec_[0].ln1_b, x_dec_ + (size_t)m.b0 * d, h_dec_ + (size_t)m.b0 * d, d,
+                               boundary_ticket_ + i, m.s);
+          launches_ += 1;
+        } else {
+          launch_argmax_finalize(st, p.part_val, p.part_idx, logits_tiles_, logits_tiles_, m.nb, kTextCtx, cfg_.eot, honor_eot, kSotLen, m.s);
+          launch_advance_step(step_ctr_ + i, m.s, /*pdl=*/true);  // this micro-batch's own step counter
+          launches_ += 2;
+        }
       }
     }
   }  // fused steps
@@ -716,6 +717,15 @@ void Engine::enqueue_decode_step(int B, bool want_logits, bool finalize, int hon
     CUDA_CHECK(cudaEventRecord(step_events_[i], mb[i].s));
     CUDA_CHECK(cudaStreamWaitEvent(stream_, step_events_[i], 0));
   }
+}
+
+// embedding of the current position + LayerNorm 1 of the first block for slots [0, B) (start of a decode, or after an EOT
+// compaction; every other step gets them from the previous step's boundary kernel)
+void Engine::enqueue_embed_ln(int B) {
+  DecodeState st = st_;  // all micro-batch step counters agree between steps: counter 0 serves the whole slot list
+  launch_embed(st, emb_f32_, pos_text_, x_dec_, B, cfg_.d, kTextCtx, stream_, /*pdl=*/false);
+  launch_layernorm(x_dec_, dec_[0].ln1_g, dec_[0].ln1_b, h_dec_, B, cfg_.d, stream_);
+  launches_ += 2;
 }
 
 void Engine::run_cross_attention_only(int B) {
@@ -788,7 +798,7 @@ int Engine::run_decode(int B, const std::vector<int>& sot, const DecodeOptions& 
     cudaGraphExec_t exec = nullptr;
     CUDA_CHECK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
     const long before = launches_;
-    enqueue_decode_step(B, false, true, opt.honor_eot ? 1 : 0, k);
+    enqueue_decode_step(B, false, true, opt.honor_eot ? 1 : 0, k, /*need_embed=*/false);
     per_step_launches_[key] = launches_ - before;
     launches_ = before;  // capture does not launch
     CUDA_CHECK(cudaStreamEndCapture(stream_, &g));
@@ -817,17 +827,21 @@ int Engine::run_decode(int B, const std::vector<int>& sot, const DecodeOptions& 
   std::vector<int> active(B);  // sequences still decoding, in slot order
   for (int b = 0; b < B; ++b) active[b] = b;
   static const bool compact = getenv("B200W_NO_COMPACT") == nullptr;
+  bool need_embed = true;  // first step, and the first one after the slot list changed: nobody has produced x / h for it yet
   while (steps_done < n_steps) {
     int k = 1;
     const int Ba = (int)active.size();
     if (graph) {
       k = (n_steps - steps_done >= graph_steps_) ? graph_steps_ : 1;
+      if (need_embed) enqueue_embed_ln(Ba);  // the graphs start from a ready x / h (their boundary kernels keep it so)
+      need_embed = false;
       const auto ge = get_graph(Ba, k);
       CUDA_CHECK(cudaGraphLaunch(ge.first, stream_));
       launches_ += ge.second;
     } else {
       const int s = steps_done;
-      enqueue_decode_step(Ba, want_logits, true, opt.honor_eot ? 1 : 0);
+      enqueue_decode_step(Ba, want_logits, true, opt.honor_eot ? 1 : 0, 1, need_embed);
+      need_embed = false;
       if (want_logits && s >= kSotLen - 1 && s - (kSotLen - 1) < max_new) {
         // logits after consuming position s = prediction of generated token (s - 3)
         const size_t step_i = (size_t)(s - (kSotLen - 1));
@@ -859,6 +873,7 @@ int Engine::run_decode(int B, const std::vector<int>& sot, const DecodeOptions& 
         CUDA_CHECK(cudaMemcpyAsync(slot_seq_, pinned_map_, sizeof(int) * still.size(), cudaMemcpyHostToDevice, stream_));
         slot_map_identity_ = false;
         active.swap(still);
+        need_embed = true;  // rows are per slot: the boundary kernel's x / h belong to the old slot list
         ++compactions_;
         if (graphs_.size() > 48) {  // many distinct batch sizes over time: start the graph cache over
           CUDA_CHECK(cudaStreamSynchronize(stream_));

@@ -132,20 +132,21 @@ class Engine {
   void import_cache(__nv_bfloat16* cache, int T, int B, int n_rows, const float* in);
   void allocate_workspace(int new_cap, long new_stride);
   void build_plans();
-  void enqueue_decode_step(int B, bool want_logits, bool finalize, int honor_eot, int n_fused = 1);
+  void enqueue_decode_step(int B, bool want_logits, bool finalize, int honor_eot, int n_fused = 1, bool need_embed = true);
+  void enqueue_embed_ln(int B);
 
   ModelConfig cfg_;
   int device_ = 0;
   cudaStream_t stream_ = nullptr;
   cudaStream_t stream2_ = nullptr;          // second micro-batch of a decoder step
   int* step_ctr_ = nullptr;                 // [4] decoder position of each micro-batch
+  int* boundary_ticket_ = nullptr;          // [4] arrival counters of the step-boundary kernels
   int graph_steps_ = 8;                     // decoder steps captured per CUDA graph (B200W_GRAPH_STEPS)
   int* cross_work_ = nullptr;               // [l_dec][4 micro-batches][2] work counters (+ one pair for time_stage)
   int prio_high_ = 0;                       // most urgent launch priority of the device (cudaDeviceGetStreamPriorityRange)
   std::vector<cudaEvent_t> step_events_;    // fork / join / per-layer cross-attention hand-over
   std::vector<cudaEvent_t> copy_events_;    // per encoder sub-batch: its PCM has been copied (pipelined transcribe())
   bool micro_batch_ = true;
-  bool fused_ln_ = false;                   // residual GEMMs of the decoder step apply the following LayerNorm (gemm_resid_ln.cu)
   int n_micro_batch_ = 2;                   // micro-batches of a decoder step (B200W_N_MICROBATCH, 1..4)
   bool cross_chain_forced_ = false;         // B200W_CROSS_CHAIN: hand over regardless of the launch size
   bool cross_chain_ = true;                 // hand the cross-attention kernels over micro-batch to micro-batch with events

@@ -35,8 +35,6 @@ using namespace gemm_detail;
 void gemm2cta_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* to, const CUtensorMap* to2, int epilogue, int n_batch,
                      int n_taps, int kb_per_tap, const int* a_c0, const int* a_row, const int* w_k0, const GemmParams& p, cudaStream_t stream);
 void gemm2cta_set_attributes();
-void gemm_resid_ln_set_attributes();
-void gemm_resid_ln_launch(const CUtensorMap& ta, const CUtensorMap& tb, int num_k_blocks, const GemmParams& p, cudaStream_t stream);
 
 namespace {
 
@@ -299,7 +297,6 @@ void set_attr_epi() {
 
 void gemm_set_attributes() {
   gemm2cta_set_attributes();
-  gemm_resid_ln_set_attributes();
   set_attr_epi<EPI_BIAS_BF16>();
   set_attr_epi<EPI_BIAS_GELU_BF16>();
   set_attr_epi<EPI_BIAS_F32>();
@@ -380,11 +377,6 @@ void gemm_launch(const GemmPlan* plan, const GemmParams& p, cudaStream_t stream)
     gemm2cta_launch(plan->tmap_a, plan->tmap_b, plan->has_out ? &plan->tmap_out : nullptr, plan->has_out ? &plan->tmap_out2 : nullptr,
                     plan->epilogue, plan->geom.n_batch, plan->geom.n_taps, plan->geom.kb_per_tap, plan->geom.a_c0, plan->geom.a_row,
                     plan->geom.w_k0, p, stream);
-    return;
-  }
-  if (plan->epilogue == EPI_RESID_LN_F32) {  // cluster kernel of gemm_resid_ln.cu (plain GEMM, 64-column tiles)
-    if (plan->block_n != 64 || plan->geom.n_taps != 1) throw CudaError("gemm: the fused residual + LayerNorm epilogue needs a plain GEMM plan with block_n 64");
-    gemm_resid_ln_launch(plan->tmap_a, plan->tmap_b, plan->geom.num_k_blocks, p, stream);
     return;
   }
   GemmGeom g = plan->geom;

@@ -43,9 +43,6 @@ enum GemmEpilogue : int {
   EPI_GELU_POS_F32 = 4,    // out f32  = gelu(acc + bias) + pos[row_in_batch][n]   (conv2 + positional embedding)
   EPI_CROSSKV_BF16 = 5,    // head-major bf16 scatter of the stacked cross-attention K/V projections
   EPI_ARGMAX = 6,          // per-row (max, first index) over this tile's columns -> partials (+ optional f32 logits)
-  EPI_RESID_LN_F32 = 7,    // out f32 += acc + bias, then ln_out bf16 = LayerNorm(out row) * gamma + beta: the residual update and the
-                           // LayerNorm that follows it in one kernel.  One thread-block cluster = all N tiles of a row block; the row
-                           // statistics are exchanged through distributed shared memory (decoder-step GEMMs, N = d <= 1024).
 };
 
 struct GemmOperandA {  // activation operand, viewed as [n_batch][rows][K] with arbitrary (16 B-multiple) pitches
@@ -81,11 +78,6 @@ struct GemmParams {
   __nv_bfloat16* cross_k;  // [L][B][H][T][64]
   __nv_bfloat16* cross_v;
   int d_model, n_head, n_ctx_kv, kv_batch, kv_batch_offset;
-  // EPI_RESID_LN_F32: LayerNorm applied to the updated residual rows (eps 1e-5), written as bf16 [rows][N] with pitch ln_ldo
-  const float* ln_gamma;
-  const float* ln_beta;
-  __nv_bfloat16* ln_out;
-  long ln_ldo;
   // EPI_ARGMAX
   float* part_val;       // [rows][n_tiles]
   int* part_idx;
@@ -106,9 +98,6 @@ GemmPlan* gemm_plan_create(const GemmOperandA& a, const __nv_bfloat16* w, int n_
                            const GemmTmaOut* out = nullptr);
 void gemm_plan_destroy(GemmPlan*);
 void gemm_launch(const GemmPlan* plan, const GemmParams& p, cudaStream_t stream);
-// whether the fused residual + LayerNorm epilogue (EPI_RESID_LN_F32) can run for this width: needs d / 64 <= 16 CTAs per cluster
-// and a device that can co-schedule such a cluster
-bool gemm_resid_ln_supported(int d);
 // plain SIMT comparator used by the self-tests only (same operand conventions, f32 output = acc + bias)
 void gemm_reference_simt(const __nv_bfloat16* a, long lda, const __nv_bfloat16* w, long ldw, const float* bias, float* out,
                          long ldo, int M, int N, int K, cudaStream_t stream);
@@ -153,6 +142,11 @@ void launch_cross_attention_decode(const float* q, const __nv_bfloat16* k, const
 void launch_advance_step(int* step, cudaStream_t stream, bool pdl = true);  // *step += 1 (once per decoder step)
 void launch_argmax_finalize(const DecodeState& st, const float* part_val, const int* part_idx, int n_tiles, int part_ld, int B,
                             int n_text_ctx, int eot, int honor_eot, int sot_len, cudaStream_t stream);
+// step boundary = argmax_finalize + advance_step + embed of the NEXT position + its first LayerNorm in one kernel (one CTA per slot;
+// ticket: one zero-initialised int owned by this launch site).  x f32 [B][d], h bf16 [B][d] = LayerNorm(x) with ln_g / ln_b.
+void launch_step_boundary(const DecodeState& st, const float* part_val, const int* part_idx, int n_tiles, int part_ld, int B, int n_text_ctx,
+                          int eot, int honor_eot, int sot_len, const float* tok_emb, const float* pos_emb, const float* ln_g, const float* ln_b,
+                          float* x, __nv_bfloat16* h, int d, int* ticket, cudaStream_t stream);
 int cross_attention_pick_split(int B, int n_head, int T);
 // K/V cache import / export at the model-ABI boundary: f32 token-major [n_seq][T][H*64] (the reference's tensors) <-> the
 // resident bf16 head-major [n_seq][H][T][64]; rows [0, n_rows) of every sequence.

@@ -355,7 +355,8 @@ int b200w_mel_tables(int n_mels, float* bank, float* window) {
   return 0;
 }
 
-// tcgen05 attention against the mma.sync comparator kernel on random bf16 q/k/v ([B*T][3d], head_dim 64).
+// tcgen05 attention against the mma.sync comparator kernel (every element) AND an fp64 host evaluation (sample rows) on random
+// bf16 q/k/v ([B*T][3d], head_dim 64).
 int b200w_selftest_attention(int B, int T, int n_head, unsigned seed, float* max_abs_diff, float* max_abs_ref) {
   if (!max_abs_diff || !max_abs_ref) return -1;
   return guarded([&] {
@@ -389,6 +390,32 @@ int b200w_selftest_attention(int B, int T, int n_head, unsigned seed, float* max
       if (!(y == y)) md = 1e9;  // NaN
       md = std::max(md, (double)fabsf(x - y));
       mr = std::max(mr, (double)fabsf(x));
+    }
+    // independent of any CUDA code: fp64 host softmax(q k^T / 8) v for sample (chunk, head, query) rows of the tcgen05 output
+    for (int smp = 0; smp < 12; ++smp) {
+      const int bb = (int)(rng() % (unsigned)B), hh = (int)(rng() % (unsigned)n_head);
+      const int qi = smp == 0 ? 0 : smp == 1 ? T - 1 : (int)(rng() % (unsigned)T);
+      auto at = [&](int t, int which, int i) { return (double)__bfloat162float(h[((size_t)bb * T + t) * 3 * d + (size_t)which * d + hh * 64 + i]); };
+      std::vector<double> sc(T);
+      double mx = -1e300;
+      for (int t = 0; t < T; ++t) {
+        double acc = 0;
+        for (int i = 0; i < 64; ++i) acc += at(qi, 0, i) * at(t, 1, i);
+        sc[t] = acc * 0.125;
+        mx = std::max(mx, sc[t]);
+      }
+      double l = 0;
+      std::vector<double> o(64, 0.0);
+      for (int t = 0; t < T; ++t) {
+        const double p = std::exp(sc[t] - mx);
+        l += p;
+        for (int i = 0; i < 64; ++i) o[i] += p * at(t, 2, i);
+      }
+      for (int i = 0; i < 64; ++i) {
+        const double ref = o[i] / l;
+        md = std::max(md, fabs((double)__bfloat162float(b[((size_t)bb * T + qi) * d + hh * 64 + i]) - ref));
+        mr = std::max(mr, fabs(ref));
+      }
     }
     *max_abs_diff = (float)md;
     *max_abs_ref = (float)mr;
@@ -490,7 +517,7 @@ int b200w_selftest_cross_attention(int B, int n_head, int T, unsigned seed, floa
   });
 }
 
-// tcgen05 GEMM vs SIMT comparator on random bf16 data.  Epilogues covered here: EPI_BIAS_F32 (2), EPI_BIAS_BF16 (0),
+// tcgen05 GEMM vs the SIMT comparator (every element) and vs an fp64 host evaluation (sample rows) on random bf16 data.  Epilogues covered here: EPI_BIAS_F32 (2), EPI_BIAS_BF16 (0),
 // EPI_BIAS_GELU_BF16 (1), EPI_BIAS_RESID_F32 (3), EPI_ARGMAX (6).
 int b200w_selftest_gemm(int M, int N, int K, int block_n, int epilogue, unsigned seed, float* max_abs_diff, float* max_abs_ref) {
   if (!max_abs_diff || !max_abs_ref) return -1;
@@ -537,21 +564,6 @@ int b200w_selftest_gemm(int M, int N, int K, int block_n, int epilogue, unsigned
     GemmPlan* plan = gemm_plan_create(a, dw, Npad, two_cta ? 256 : block_n, epilogue, two_cta);
     GemmParams p{};
     p.rows_valid = M, p.N = N, p.ldo = N, p.bias = db, p.n_batch = 1;
-    // fused residual + LayerNorm epilogue: random gamma / beta, bf16 LayerNorm output next to the updated f32 rows
-    std::vector<float> hg(N), hbeta(N);
-    for (int n = 0; n < N; ++n) hg[n] = 1.f + 0.1f * nd(rng), hbeta[n] = 0.1f * nd(rng);
-    float *dg = nullptr, *dbeta = nullptr;
-    __nv_bfloat16* dln = nullptr;
-    if (epilogue == EPI_RESID_LN_F32) {
-      if (!gemm_resid_ln_supported(N)) throw std::runtime_error("unsupported: this device cannot co-schedule the cluster the fused LayerNorm epilogue needs");
-      CUDA_CHECK(cudaMalloc(&dg, N * 4));
-      CUDA_CHECK(cudaMalloc(&dbeta, N * 4));
-      CUDA_CHECK(cudaMalloc(&dln, (size_t)M * N * 2));
-      CUDA_CHECK(cudaMemcpy(dg, hg.data(), N * 4, cudaMemcpyHostToDevice));
-      CUDA_CHECK(cudaMemcpy(dbeta, hbeta.data(), N * 4, cudaMemcpyHostToDevice));
-      CUDA_CHECK(cudaMemset(dln, 0xff, (size_t)M * N * 2));
-      p.ln_gamma = dg, p.ln_beta = dbeta, p.ln_out = dln, p.ln_ldo = N;
-    }
     const bool bf_out = epilogue == EPI_BIAS_BF16 || epilogue == EPI_BIAS_GELU_BF16;
     p.out = bf_out ? (void*)dout_bf : (void*)dout;
     p.part_val = dpv, p.part_idx = dpi, p.part_ld = n_tiles;
@@ -591,29 +603,6 @@ int b200w_selftest_gemm(int M, int N, int K, int block_n, int epilogue, unsigned
         }
         if (pbi != bi) md = std::max(md, 1e9);  // flag an argmax mismatch loudly
       }
-    } else if (epilogue == EPI_RESID_LN_F32) {
-      // host: x = resid + (A W^T + bias) [the SIMT comparator's f32 product], h = LayerNorm(x) * gamma + beta in fp64
-      std::vector<__nv_bfloat16> hl((size_t)M * N);
-      CUDA_CHECK(cudaMemcpy(hl.data(), dln, hl.size() * 2, cudaMemcpyDeviceToHost));
-      for (int m = 0; m < M; ++m) {
-        double mean = 0, var = 0;
-        for (int n = 0; n < N; ++n) mean += (double)ref[(size_t)m * N + n] + hres[(size_t)m * N + n];
-        mean /= N;
-        for (int n = 0; n < N; ++n) {
-          const double x = (double)ref[(size_t)m * N + n] + hres[(size_t)m * N + n] - mean;
-          var += x * x;
-        }
-        const double rstd = 1.0 / sqrt(var / N + 1e-5);
-        for (int n = 0; n < N; ++n) {
-          const double x = (double)ref[(size_t)m * N + n] + hres[(size_t)m * N + n];
-          const double h = (x - mean) * rstd * hg[n] + hbeta[n];
-          const float gh = __bfloat162float(hl[(size_t)m * N + n]);
-          if (!(gh == gh)) md = 1e9;
-          md = std::max(md, fabs((double)got[(size_t)m * N + n] - x));  // the updated residual row
-          md = std::max(md, fabs((double)gh - h));                       // its LayerNorm (bf16)
-          mr = std::max(mr, fabs(h));
-        }
-      }
     } else {
       for (size_t i = 0; i < ref.size(); ++i) {
         float r = ref[i];
@@ -623,12 +612,28 @@ int b200w_selftest_gemm(int M, int N, int K, int block_n, int epilogue, unsigned
         mr = std::max(mr, (double)fabsf(r));
       }
     }
+    // independent of any CUDA code: fp64 host evaluation of sample rows from the same bf16 inputs (the SIMT comparator above
+    // covers every element; this pins both kernels to the definition C = A W^T + bias)
+    {
+      std::vector<int> rows = {0, M / 3, (2 * M) / 3, M - 1};
+      for (int i = 0; i < 4; ++i) rows.push_back((int)(rng() % (unsigned)M));
+      for (int m : rows) {
+        for (int n = 0; n < N; ++n) {
+          double acc = hb[n];
+          for (int k = 0; k < K; ++k) acc += (double)__bfloat162float(ha[(size_t)m * K + k]) * (double)__bfloat162float(hw[(size_t)n * K + k]);
+          if (epilogue == EPI_BIAS_GELU_BF16) acc = 0.5 * acc * (1.0 + erf(acc * 0.7071067811865476));
+          if (epilogue == EPI_BIAS_RESID_F32) acc += hres[(size_t)m * N + n];
+          const double g = got[(size_t)m * N + n];
+          const double tol_bf16 = (epilogue == EPI_BIAS_BF16 || epilogue == EPI_BIAS_GELU_BF16) ? fabs(acc) * 0.00390625 : 0.0;  // 2^-8: bf16 output
+          md = std::max(md, std::max(0.0, fabs(g - acc) - tol_bf16));
+        }
+      }
+    }
     *max_abs_diff = (float)md;
     *max_abs_ref = (float)mr;
     gemm_plan_destroy(plan);
     cudaStreamDestroy(s);
     cudaFree(da), cudaFree(dw), cudaFree(db), cudaFree(dref), cudaFree(dout), cudaFree(dout_bf), cudaFree(dpv), cudaFree(dpi);
-    cudaFree(dg), cudaFree(dbeta), cudaFree(dln);
   });
 }
 
