@@ -229,6 +229,17 @@ def workload_config(args, world):
 class Dist:
     def __init__(self, rank, local_rank, world):
         self.rank, self.local_rank, self.world = rank, local_rank, world
+        self.cpu_group = None
+        if world > 1:
+            import torch.distributed as dist
+
+            self.cpu_group = dist.new_group(backend="gloo")  # host-side waits that leave the GPUs idle (an NCCL barrier spins on them)
+
+    def host_barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.barrier(group=self.cpu_group)
 
     def barrier(self):
         import torch
@@ -439,6 +450,8 @@ def main():
     all_toks = dd.gather_tokens(toks_resident, args.new_tokens)
     if not args.no_extras and args.config == 2 and world > 1:
         lib = None
+        dd.barrier()
+        dd.host_barrier()
         if rank == 0:
             try:
                 os.environ["B200W_DEVICES"] = ",".join(str(i) for i in range(world))
@@ -457,15 +470,18 @@ def main():
                     ts.append(time.perf_counter() - t2)
                 wl.close()
                 ref = [list(map(int, row)) for a in all_toks for row in a]
+                bad = [(i, next((k for k in range(min(len(got[i]), len(ref[i]))) if got[i][k] != ref[i][k]), -1)) for i in range(len(ref)) if got[i] != ref[i]]
                 lib = {"handle": "one AX_WHISPER handle, B200W_DEVICES=%s, one engine + host thread per GPU" % os.environ["B200W_DEVICES"],
                        "chunks": len(big), "wall_s": min(ts), "audio_s_per_s": CHUNK_S * len(big) / min(ts), "host_buffers": "pageable",
-                       "tokens_equal_per_rank_result": got == ref}
-                assert got == ref, "library multi-GPU path and the per-rank engines disagree on the token ids"
+                       "tokens_equal_per_rank_result": not bad}
+                if bad:
+                    lib["mismatches"] = {"count": len(bad), "per_rank": [sum(1 for i, _ in bad if i // B == rr) for rr in range(world)],
+                                         "first": bad[:8], "local_half_equal": got[:B] == toks_resident}
             except Exception as ex:  # the headline line must survive a failing extra
                 lib = {"error": "%s: %s" % (type(ex).__name__, ex)}
             finally:
                 os.environ.pop("B200W_DEVICES", None)
-        dd.barrier()
+        dd.host_barrier()  # the other ranks wait on the host: their GPUs belong to rank 0's handle meanwhile
         if rank == 0:
             extra["library_dp"] = lib
 

@@ -23,6 +23,10 @@ struct GemmGeom {
   // a_c0[t] + k, rows row + a_row[t]) against W columns w_k0[t] + k.  A plain GEMM has one tap.
   int n_taps, kb_per_tap;
   int a_c0[3], a_row[3], w_k0[3];
+  // bytes TMA delivers per A stage: 128 rows x 128 B normally; a decoder-step GEMM over M <= 32 / 64 rows loads only a 32- / 64-row
+  // box (the tensor core still multiplies 128 rows: the rest of the stage is stale shared memory whose accumulator rows are
+  // never stored).  Every CTA of such a GEMM reads the whole A from L2, so this cuts its operand traffic up to 4x.
+  int a_stage_bytes;
 };
 
 // Epilogue of one accumulator tile, executed by all kEpiWarps epilogue warps of a CTA (epi_warp = 0..kEpiWarps-1, its

@@ -113,7 +113,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int n_pre = g.num_k_blocks < kStages ? g.num_k_blocks : kStages;
     for (int ks = 0; ks < n_pre; ++ks) {
       const int tap = ks / g.kb_per_tap, kb = ks - tap * g.kb_per_tap;
-      mbar_arrive_expect_tx(&full_bar[ks], Cfg::kStageBytes);
+      mbar_arrive_expect_tx(&full_bar[ks], Cfg::kStageBytesB + g.a_stage_bytes);
       tma_load_2d(smem + ks * Cfg::kStageBytes + Cfg::kStageBytesA, &tmap_b, &full_bar[ks], g.w_k0[tap] + kb * BLOCK_K, c.n_blk * BLOCK_N);
     }
     pre_issued = n_pre;
@@ -136,7 +136,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               --pre_issued;
             } else {
               mbar_wait(&empty_bar[stage], phase ^ 1);
-              mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+              mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytesB + g.a_stage_bytes);
               tma_load_2d(sb, &tmap_b, &full_bar[stage], g.w_k0[tap] + kb * BLOCK_K, c.n_blk * BLOCK_N);
             }
             tma_load_3d(sa, &tmap_a, &full_bar[stage], g.a_c0[tap] + kb * BLOCK_K, c.m_blk * BLOCK_M + g.a_row[tap] + p.a_row_offset, c.batch + p.a_batch_offset);
@@ -308,6 +308,7 @@ void gemm_set_attributes() {
 
 struct GemmPlan {
   CUtensorMap tmap_a, tmap_b;
+  CUtensorMap tmap_a_thin[2];  // A boxes of 32 and 64 rows (1-CTA kernel, single row block of <= 32 / 64 valid rows)
   GemmGeom geom;
   int block_n, epilogue, grid;
   bool two_cta;
@@ -325,6 +326,10 @@ GemmPlan* gemm_plan_create(const GemmOperandA& a, const __nv_bfloat16* w, int n_
   const uint64_t apitch[2] = {(uint64_t)a.row_pitch * 2, (uint64_t)(a.n_batch > 1 ? a.batch_pitch : (long)a.rows * a.row_pitch) * 2};
   const uint32_t abox[3] = {BLOCK_K, BLOCK_M, 1};
   pl->tmap_a = make_tmap(a.ptr, 3, adims, apitch, abox);
+  for (int i = 0; i < 2; ++i) {
+    const uint32_t tbox[3] = {BLOCK_K, i == 0 ? 32u : 64u, 1};
+    pl->tmap_a_thin[i] = (uint64_t)a.rows >= tbox[1] ? make_tmap(a.ptr, 3, adims, apitch, tbox) : pl->tmap_a;
+  }
   const int n_taps = a.n_taps > 0 ? a.n_taps : 1;
   const int k_per_tap = a.n_taps > 0 ? a.k_per_tap : a.K;
   const long w_k = (long)n_taps * k_per_tap;  // W is [n_rows_w][n_taps * k_per_tap], row-major
@@ -386,14 +391,23 @@ void gemm_launch(const GemmPlan* plan, const GemmParams& p, cudaStream_t stream)
   g.total_tiles = g.n_batch * g.m_tiles_per_batch * g.n_tiles;
   if (g.total_tiles <= 0) return;
   const int grid = g.total_tiles < kNumSMs ? g.total_tiles : kNumSMs;
+  // thin A operand for the decoder-step shapes (one row block with few valid rows): a 32- or 64-row TMA box
+  static const bool thin_ok = getenv("B200W_NO_THIN_A") == nullptr;
+  const CUtensorMap* ta = &plan->tmap_a;
+  g.a_stage_bytes = BLOCK_M * BLOCK_K * 2;
+  if (thin_ok && g.m_tiles_per_batch == 1 && g.n_batch == 1 && g.n_taps == 1 && p.rows_valid <= 64) {
+    const int rows = p.rows_valid <= 32 ? 32 : 64;
+    ta = &plan->tmap_a_thin[rows == 32 ? 0 : 1];
+    g.a_stage_bytes = rows * BLOCK_K * 2;
+  }
   switch (plan->epilogue) {
-    case EPI_BIAS_BF16: launch_bn<EPI_BIAS_BF16>(plan->block_n, plan->tmap_a, plan->tmap_b, g, p, grid, stream); break;
-    case EPI_BIAS_GELU_BF16: launch_bn<EPI_BIAS_GELU_BF16>(plan->block_n, plan->tmap_a, plan->tmap_b, g, p, grid, stream); break;
-    case EPI_BIAS_F32: launch_bn<EPI_BIAS_F32>(plan->block_n, plan->tmap_a, plan->tmap_b, g, p, grid, stream); break;
-    case EPI_BIAS_RESID_F32: launch_bn<EPI_BIAS_RESID_F32>(plan->block_n, plan->tmap_a, plan->tmap_b, g, p, grid, stream); break;
-    case EPI_GELU_POS_F32: launch_bn<EPI_GELU_POS_F32>(plan->block_n, plan->tmap_a, plan->tmap_b, g, p, grid, stream); break;
-    case EPI_CROSSKV_BF16: launch_bn<EPI_CROSSKV_BF16>(plan->block_n, plan->tmap_a, plan->tmap_b, g, p, grid, stream); break;
-    case EPI_ARGMAX: launch_bn<EPI_ARGMAX>(plan->block_n, plan->tmap_a, plan->tmap_b, g, p, grid, stream); break;
+    case EPI_BIAS_BF16: launch_bn<EPI_BIAS_BF16>(plan->block_n, *ta, plan->tmap_b, g, p, grid, stream); break;
+    case EPI_BIAS_GELU_BF16: launch_bn<EPI_BIAS_GELU_BF16>(plan->block_n, *ta, plan->tmap_b, g, p, grid, stream); break;
+    case EPI_BIAS_F32: launch_bn<EPI_BIAS_F32>(plan->block_n, *ta, plan->tmap_b, g, p, grid, stream); break;
+    case EPI_BIAS_RESID_F32: launch_bn<EPI_BIAS_RESID_F32>(plan->block_n, *ta, plan->tmap_b, g, p, grid, stream); break;
+    case EPI_GELU_POS_F32: launch_bn<EPI_GELU_POS_F32>(plan->block_n, *ta, plan->tmap_b, g, p, grid, stream); break;
+    case EPI_CROSSKV_BF16: launch_bn<EPI_CROSSKV_BF16>(plan->block_n, *ta, plan->tmap_b, g, p, grid, stream); break;
+    case EPI_ARGMAX: launch_bn<EPI_ARGMAX>(plan->block_n, *ta, plan->tmap_b, g, p, grid, stream); break;
     default: throw CudaError("gemm: unknown epilogue");
   }
 }
