@@ -379,8 +379,8 @@ void Engine::free_workspace() {
   // the engine is EMPTY from here until ensure_capacity() has rebuilt everything: a failed re-allocation must not leave
   // capacities that describe freed memory
   cap_ = 0, pcm_stride_ = 0, enc_sub_ = 0, dec_rows_pad_ = 0;
-  pcm_ = mel_ = utt_max_ = x_enc_ = x_dec_ = qkv_dec_ = q_dec_ = logits_ = part_val_ = nullptr;
-  n_samples_ = part_idx_ = cross_work_ = step_ctr_ = slot_seq_ = boundary_ticket_ = nullptr;
+  pcm_ = mel_ = x_enc_ = x_dec_ = qkv_dec_ = q_dec_ = logits_ = part_val_ = nullptr;
+  n_samples_ = part_idx_ = cross_work_ = step_ctr_ = slot_seq_ = boundary_ticket_ = utt_state_ = nullptr;
   mel_tm_ = conv1_out_ = h_enc_ = qkv_enc_ = attn_enc_ = mlp_enc_ = cross_k_ = cross_v_ = self_k_ = self_v_ = nullptr;
   h_dec_ = attn_dec_ = mlp_dec_ = nullptr;
   st_ = DecodeState{};
@@ -413,7 +413,7 @@ void Engine::allocate_workspace(int new_cap, long new_stride) {
   auto& o = ws_owned_;
   pcm_ = dev_alloc<float>(o, (size_t)cap_ * pcm_stride_, false);
   n_samples_ = dev_alloc<int>(o, cap_);
-  utt_max_ = dev_alloc<float>(o, cap_);
+  utt_state_ = dev_alloc<int>(o, 2 * (size_t)cap_ + 1);
   mel_ = dev_alloc<float>(o, (size_t)cap_ * cfg_.n_mels * kMelFrames);
   mel_tm_ = dev_alloc<__nv_bfloat16>(o, (size_t)cap_ * (kMelFrames + 2) * cfg_.n_mels);
   conv1_out_ = dev_alloc<__nv_bfloat16>(o, (size_t)enc_sub_ * (kMelFrames + 2) * d);
@@ -523,8 +523,8 @@ void Engine::build_plans() {
 void Engine::run_logmel(int B, int max_samples) { run_logmel_range(0, B, max_samples); }
 void Engine::run_logmel_range(int b0, int nb, int max_samples) {
   launch_logmel(pcm_ + (size_t)b0 * pcm_stride_, pcm_stride_, n_samples_ + b0, max_samples, nb, cfg_.n_mels,
-                mel_ + (size_t)b0 * cfg_.n_mels * kMelFrames, mel_tm_ + (size_t)b0 * (kMelFrames + 2) * cfg_.n_mels, utt_max_ + b0, stream_);
-  launches_ += 3;
+                mel_ + (size_t)b0 * cfg_.n_mels * kMelFrames, mel_tm_ + (size_t)b0 * (kMelFrames + 2) * cfg_.n_mels, utt_state_ + 2 * (size_t)b0, stream_);
+  launches_ += 1;
 }
 void Engine::run_mel_convert(int B) {
   launch_mel_to_timemajor(mel_, B, cfg_.n_mels, mel_tm_, stream_);

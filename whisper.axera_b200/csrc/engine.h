@@ -168,8 +168,8 @@ class Engine {
   std::vector<LayerDec> dec_;
 
   // workspace (device), sized for cap_
-  float *pcm_ = nullptr, *mel_ = nullptr, *utt_max_ = nullptr;
-  int* n_samples_ = nullptr;
+  float *pcm_ = nullptr, *mel_ = nullptr;
+  int *n_samples_ = nullptr, *utt_state_ = nullptr;  // utt_state_: [cap][2] per-utterance scratch of the log-mel kernel
   __nv_bfloat16 *mel_tm_ = nullptr, *conv1_out_ = nullptr;
   float* x_enc_ = nullptr;
   __nv_bfloat16 *h_enc_ = nullptr, *qkv_enc_ = nullptr, *attn_enc_ = nullptr, *mlp_enc_ = nullptr;

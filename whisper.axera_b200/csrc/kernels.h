@@ -28,9 +28,9 @@ inline void kernels_set_attributes() {
 void logmel_upload_tables();
 size_t logmel_mel_table_copy(int n_mels, float* dense_bank, float* window400);
 // pcm [B][pcm_stride] f32 (device), n_samples_dev [B]; out_mel [B][n_mels][3000] f32; out_tm bf16
-// [B][3002][n_mels] (may be null); utt_max_scratch [B] f32.
+// [B][3002][n_mels] (may be null); utt_state [2 B + 1] int scratch (per utterance: running maximum key, arrivals; + the block-ticket counter).  One memset + ONE kernel.
 void launch_logmel(const float* pcm, long pcm_stride, const int* n_samples_dev, int max_samples, int B, int n_mels,
-                   float* out_mel, __nv_bfloat16* out_tm, float* utt_max_scratch, cudaStream_t stream);
+                   float* out_mel, __nv_bfloat16* out_tm, int* utt_state, cudaStream_t stream);
 void launch_mel_to_timemajor(const float* mel, int B, int n_mels, __nv_bfloat16* out_tm, cudaStream_t stream);
 
 // ---- K4 tcgen05 GEMM (gemm_tcgen05.cu) ------------------------------------------------------------

@@ -99,25 +99,92 @@ struct __align__(16) LogmelSmem {
   float red[kThreads / 32];
 };
 
-__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
-  if (v >= 0.f)
-    atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
-  else
-    atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+// Per-utterance state of one launch, two ints: [0] running maximum as an order-preserving integer key, [1] arrivals of its frame
+// blocks; one more int after the last utterance hands out the block tickets.
+// Both start from the byte pattern 0x80 (one cudaMemsetAsync): as a key that is -3.4e38, below every log-mel value.
+constexpr int kStateInit = (int)0x80808080;
+__device__ __forceinline__ int float_key(float v) {
+  const int k = __float_as_int(v);
+  return k >= 0 ? k : k ^ 0x7fffffff;  // monotonic in v, an involution
+}
+__device__ __forceinline__ float key_float(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
+
+constexpr int kNormFrames = 32;  // frames per tile of the normalisation pass: 128-byte rows of the [n_mels][3000] tensor
+constexpr int kNormCtas = 12;    // normalisation CTAs per utterance (94 tiles of 32 frames between them)
+
+// Normalisation CTA `part` (0 .. kNormCtas-1) of utterance b: waits until every frame CTA of the utterance has arrived, then
+// normalises its share of the 3000 output frames against the utterance maximum and writes the bf16 time-major copy.
+// These CTAs sit at the END of the utterance's blockIdx.x range: blocks are dispatched in order, so by the time one of them
+// runs, every frame CTA it waits for has been dispatched (they never wait on anything) -- the wait cannot deadlock.
+// (max(L, float(mmax - 8.0)) + 4.0) / 4.0 is evaluated in double by the reference (Whisper.cpp:171); L + 4 is exact in double
+// and /4 is a power-of-two scaling, so the float result equals fl32(L + 4) * 0.25 exactly.
+__device__ __forceinline__ void logmel_normalize_part(int b, int part, int n_frames, int n_mels, float* __restrict__ out,
+                                                      int* __restrict__ utt_state, __nv_bfloat16* __restrict__ out_tm,
+                                                      unsigned char* smem_raw) {
+  const int tid = threadIdx.x;
+  const int n_ctas = (n_frames + kFramesPerCta - 1) / kFramesPerCta;  // frame CTAs of this utterance that do arrive
+  if (tid == 0) {
+    const volatile int* tickets = utt_state + 2 * b + 1;
+    while (*tickets - kStateInit < n_ctas) __nanosleep(200);
+    __threadfence();
+  }
+  __syncthreads();
+  const float mmax = key_float(*reinterpret_cast<volatile int*>(&utt_state[2 * b]));
+  const float floor_v = __fadd_rn(mmax, -8.0f);
+  float(*tile)[kNormFrames + 1] = reinterpret_cast<float(*)[kNormFrames + 1]>(smem_raw);  // [128][33]
+  constexpr int kTiles = (kOutFrames + kNormFrames - 1) / kNormFrames;                    // 94
+  for (int t = part; t < kTiles; t += kNormCtas) {
+    const int t0 = t * kNormFrames;
+    __syncthreads();  // the previous tile's transposed reads are done
+    for (int it = tid; it < n_mels * kNormFrames; it += kThreads) {
+      const int fr = it % kNormFrames, mel = it / kNormFrames;
+      const int f = t0 + fr;
+      float v = 0.f;
+      if (f < kOutFrames) {
+        float* p = out + ((long)b * n_mels + mel) * kOutFrames + f;
+        if (f < n_frames) v = __fmul_rn(__fadd_rn(fmaxf(__ldcg(p), floor_v), 4.0f), 0.25f);
+        *p = v;  // frames past the audio are zero-filled AFTER normalisation (Whisper.cpp:172)
+      }
+      tile[mel][fr] = v;
+    }
+    if (out_tm == nullptr) continue;
+    __syncthreads();
+    for (int it = tid; it < n_mels * kNormFrames; it += kThreads) {
+      const int mel = it % n_mels, fr = it / n_mels;
+      const int f = t0 + fr;
+      if (f < kOutFrames) out_tm[((long)b * (kOutFrames + 2) + f + 1) * n_mels + mel] = __float2bfloat16_rn(tile[mel][fr]);
+    }
+  }
 }
 
-// pass 1: one CTA = kFramesPerCta consecutive STFT frames of one utterance
-__global__ void __launch_bounds__(kThreads) logmel_frames_kernel(const float* __restrict__ pcm, long pcm_stride,
-                                                                const int* __restrict__ n_samples_arr, int n_mels,
-                                                                int bank, float* __restrict__ out,
-                                                                float* __restrict__ utt_max) {
+// The whole frontend in ONE launch.  One CTA = kFramesPerCta consecutive STFT frames of one utterance: reflect-padded PCM tile ->
+// Hann window -> 400-point real FFT (the reference's kissfft butterfly order) -> |X|^2 -> mel triangles -> log10 -> global
+// memory + the utterance's running maximum.  Whisper::preprocess normalises against the maximum over ALL frames of the
+// utterance (Whisper.cpp:157-171), which only exists once every frame CTA of the utterance is done: the last kNormCtas blocks of
+// every utterance's blockIdx.x range wait for that (arrival counter) and then do the second pass -- values mostly still in L2 --
+// and write the bf16 time-major copy the first convolution reads.  (Round 1 used three launches: init, frames, normalise.)
+__global__ void __launch_bounds__(kThreads) logmel_fused_kernel(const float* __restrict__ pcm, long pcm_stride,
+                                                               const int* __restrict__ n_samples_arr, int n_mels, int bank,
+                                                               float* __restrict__ out, int* __restrict__ utt_state /* [B][2] + 1 */,
+                                                               __nv_bfloat16* __restrict__ out_tm /* [B][3002][n_mels] or null */, int n_utt) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   LogmelSmem& S = *reinterpret_cast<LogmelSmem*>(smem_raw);
-  const int b = blockIdx.y;
   const int tid = threadIdx.x;
+  // Work is handed out by an arrival ticket, not by blockIdx: a normalisation block only ever waits for blocks with LOWER
+  // tickets, i.e. blocks that are already running -- independent of the order in which the hardware dispatches blocks.
+  __shared__ int s_vid;
+  if (tid == 0) s_vid = atomicAdd(&utt_state[2 * n_utt], 1) - kStateInit;
+  __syncthreads();
+  const int per_utt = gridDim.x;  // frame blocks first, then the utterance's kNormCtas normalisation blocks
+  const int b = s_vid / per_utt, bx = s_vid - b * per_utt;
   const int n = n_samples_arr[b];
   const int n_frames = 1 + n / kHop;  // librosa.h:87 with centre padding of n_fft/2 each side
-  const int f0 = blockIdx.x * kFramesPerCta;
+  const int n_frame_ctas = per_utt - kNormCtas;
+  if (bx >= n_frame_ctas) {
+    logmel_normalize_part(b, bx - n_frame_ctas, n_frames, n_mels, out, utt_state, out_tm, smem_raw);
+    return;
+  }
+  const int f0 = bx * kFramesPerCta;
   if (f0 >= n_frames) return;
   const int nf = min(kFramesPerCta, n_frames - f0);
   const float* x = pcm + (long)b * pcm_stride;
@@ -242,48 +309,14 @@ __global__ void __launch_bounds__(kThreads) logmel_frames_kernel(const float* __
   }
   vmax = warp_max(vmax);
   if ((tid & 31) == 0) S.red[tid >> 5] = vmax;
+  __threadfence();  // this thread's log-mel values are visible device-wide before the arrival below
   __syncthreads();
   if (tid == 0) {
     float v = S.red[0];
     for (int i = 1; i < kThreads / 32; ++i) v = fmaxf(v, S.red[i]);
-    atomic_max_float(&utt_max[b], v);
-  }
-}
-
-__global__ void logmel_init_max_kernel(float* utt_max, int B) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < B) utt_max[i] = -FLT_MAX;  // Whisper.cpp:158
-}
-
-// pass 2: in-place normalisation of a [n_mels x kFramesPerCta frames] tile + bf16 time-major copy for conv1.
-// (max(L, float(mmax - 8.0)) + 4.0) / 4.0 is evaluated in double by the reference (Whisper.cpp:171); L + 4 is
-// exact in double and /4 is a power-of-two scaling, so the float result equals fl32(L + 4) * 0.25 exactly.
-__global__ void __launch_bounds__(kThreads) logmel_normalize_kernel(float* __restrict__ out, const float* __restrict__ utt_max,
-                                                                   const int* __restrict__ n_samples_arr, int n_mels,
-                                                                   __nv_bfloat16* __restrict__ out_tm /* [B][3002][n_mels] or null */) {
-  __shared__ float tile[128][kFramesPerCta + 1];
-  const int b = blockIdx.y;
-  const int f0 = blockIdx.x * kFramesPerCta;
-  const int tid = threadIdx.x;
-  const int n_frames = 1 + n_samples_arr[b] / kHop;
-  const float floor_v = __fadd_rn(utt_max[b], -8.0f);
-  for (int it = tid; it < n_mels * kFramesPerCta; it += kThreads) {
-    const int fr = it % kFramesPerCta, mel = it / kFramesPerCta;
-    const int f = f0 + fr;
-    float v = 0.f;
-    if (f < kOutFrames) {
-      float* p = out + ((long)b * n_mels + mel) * kOutFrames + f;
-      if (f < n_frames) v = __fmul_rn(__fadd_rn(fmaxf(*p, floor_v), 4.0f), 0.25f);
-      *p = v;  // frames past the audio are zero-filled AFTER normalisation (Whisper.cpp:172)
-    }
-    tile[mel][fr] = v;
-  }
-  if (out_tm == nullptr) return;
-  __syncthreads();
-  for (int it = tid; it < n_mels * kFramesPerCta; it += kThreads) {
-    const int mel = it % n_mels, fr = it / n_mels;
-    const int f = f0 + fr;
-    if (f < kOutFrames) out_tm[((long)b * (kOutFrames + 2) + f + 1) * n_mels + mel] = __float2bfloat16_rn(tile[mel][fr]);
+    atomicMax(&utt_state[2 * b], float_key(v));
+    __threadfence();
+    atomicAdd(&utt_state[2 * b + 1], 1);  // arrival: the normalisation CTAs of this utterance wait for all of them
   }
 }
 
@@ -361,20 +394,19 @@ size_t logmel_mel_table_copy(int n_mels, float* dense_bank /* [n_mels][201] host
 }
 
 void launch_logmel(const float* pcm, long pcm_stride, const int* n_samples_dev, int max_samples, int B, int n_mels,
-                   float* out_mel, __nv_bfloat16* out_tm, float* utt_max_scratch, cudaStream_t stream) {
+                   float* out_mel, __nv_bfloat16* out_tm, int* utt_state, cudaStream_t stream) {
   if (n_mels != 80 && n_mels != 128) throw CudaError("logmel: n_mels must be 80 or 128");
   const int bank = n_mels == 80 ? 0 : 1;
   const int max_frames = 1 + max_samples / kHop;
-  logmel_init_max_kernel<<<(B + 255) / 256, 256, 0, stream>>>(utt_max_scratch, B);
-  dim3 g1((max_frames + kFramesPerCta - 1) / kFramesPerCta, B);
-  logmel_frames_kernel<<<g1, kThreads, sizeof(LogmelSmem), stream>>>(pcm, pcm_stride, n_samples_dev, n_mels, bank, out_mel, utt_max_scratch);
-  dim3 g2((kOutFrames + kFramesPerCta - 1) / kFramesPerCta, B);
-  logmel_normalize_kernel<<<g2, kThreads, 0, stream>>>(out_mel, utt_max_scratch, n_samples_dev, n_mels, out_tm);
+  CUDA_CHECK(cudaMemsetAsync(utt_state, 0x80, sizeof(int) * (2 * (size_t)B + 1), stream));  // kStateInit: maxima, arrivals, block tickets
+  dim3 g1((max_frames + kFramesPerCta - 1) / kFramesPerCta + kNormCtas, B);  // frame CTAs, then the utterance's normalisation CTAs
+  logmel_fused_kernel<<<g1, kThreads, sizeof(LogmelSmem), stream>>>(pcm, pcm_stride, n_samples_dev, n_mels, bank, out_mel, utt_state, out_tm, B);
   CUDA_CHECK(cudaGetLastError());
 }
 
 void logmel_set_attributes() {
-  CUDA_CHECK(cudaFuncSetAttribute(logmel_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LogmelSmem)));
+  static_assert(sizeof(LogmelSmem) >= sizeof(float) * 128 * (kNormFrames + 1), "the normalisation tile aliases the FFT staging");
+  CUDA_CHECK(cudaFuncSetAttribute(logmel_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LogmelSmem)));
 }
 
 void launch_mel_to_timemajor(const float* mel, int B, int n_mels, __nv_bfloat16* out_tm, cudaStream_t stream) {
