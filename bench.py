@@ -382,6 +382,12 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dd = Dist(rank, local_rank, world)
+    t_start = time.perf_counter()
+
+    def phase(name):  # wall-clock trace of the run on stderr (stdout carries exactly one JSON line)
+        if rank == 0:
+            print("[bench +%6.1f s] %s" % (time.perf_counter() - t_start, name), file=sys.stderr, flush=True)
+
     pk = peaks()
     pkg = g.load_package()
     if rank == 0:
@@ -393,6 +399,7 @@ def main():
     dims = eng.dims
     d, H, L = dims.d_model, dims.n_head, dims.n_text_layer
 
+    phase("engine ready, synthetic PCM generated")
     # ---- `value`: inputs resident in HBM --------------------------------------------------------------------------
     sampler = ClockSampler(local_rank) if rank == 0 else None
     r = resident_leg(eng, pcm, B, args.new_tokens, args.steps, args.warmup, dd, sampler)
@@ -408,6 +415,7 @@ def main():
         n_it = 8
         return dd.allmax(min(eng.time_stage(3, nb, iters=n_it) for _ in range(3)) / (n_it * L))  # best of 3 x (8 x L) launches
 
+    phase("resident leg done")
     nb_step = (B + 1) // 2 if B >= 32 else B
     x_step_ms = xattn_ms(nb_step)
     x_full_ms = xattn_ms(B) if nb_step != B else x_step_ms
@@ -428,6 +436,7 @@ def main():
         extra["strong"] = strong
     eng.close()
 
+    phase("roofline kernel + strong split done")
     # ---- `e2e`: the reference-shaped C ABI (AX_WHISPER_Init / AX_WHISPER_RunPCMTokens) with pinned host buffers ---------
     os.environ["B200W_DEVICE"] = str(local_rank)
     os.environ["B200W_MAX_BATCH"] = str(B)
@@ -447,6 +456,7 @@ def main():
 
     # ---- the library's own multi-GPU path: ONE handle on rank 0 that owns an engine per GPU (B200W_DEVICES), host threads,
     # no collective; all N x B chunks through AX_WHISPER_RunPCMTokens; tokens must equal what the ranks produced ---------
+    phase("e2e leg done")
     all_toks = dd.gather_tokens(toks_resident, args.new_tokens)
     if not args.no_extras and args.config == 2 and world > 1:
         lib = None
@@ -485,6 +495,7 @@ def main():
         if rank == 0:
             extra["library_dp"] = lib
 
+    phase("library multi-GPU leg done")
     # ---- the other BASELINE configurations, compact (configs 1, 3 and the long-form 4; config 0 is the CPU report) ------
     if not args.no_extras and args.config == 2:
         others = {}
@@ -507,6 +518,7 @@ def main():
                 others["config%d" % idx] = {"error": "%s: %s" % (type(ex).__name__, ex)}
         extra["other_configs"] = others
 
+    phase("other configurations done")
     if rank == 0:
         audio_s = CHUNK_S * B * world
         value = audio_s / (step_ms / 1e3)
@@ -542,10 +554,15 @@ def main():
             "stages": {**stage_fracs(r, dims, args.arch, B, args.new_tokens, pk), "wall_ms_per_step": wall_step_s * 1e3},
         }
         if not args.no_extras and args.config == 2:
-            try:
-                extra.setdefault("other_configs", {})["config0"] = config0_report()
-            except Exception as ex:
-                extra.setdefault("other_configs", {})["config0"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
+            if world == 1:
+                try:
+                    extra.setdefault("other_configs", {})["config0"] = config0_report()
+                except Exception as ex:
+                    extra.setdefault("other_configs", {})["config0"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
+            else:
+                # a CPU report: it does not depend on N, and the other ranks' processes wait on this one meanwhile (their
+                # spinning waits and a 32-thread torch pool on the same cores slow each other down by orders of magnitude)
+                extra.setdefault("other_configs", {})["config0"] = {"note": "CPU report of configs[0]: measured in the N = 1 run (python bench.py, or --config 0)"}
         if extra:
             line["extra"] = extra
         if not args.no_cpu_baseline and world == 1:
@@ -562,9 +579,10 @@ def main():
                           "restatement of the reference's exported graphs (onnxruntime not installed)"
                           % (n_chunks, args.arch, args.new_tokens, sec,
                              "the reference's own C++ frontend (oracle/_ref)" if util.mel_ref_lib() is not None else "numpy port")}
+        phase("CPU legs done")
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
+        dd.host_barrier()  # the other ranks wait on the host while rank 0 finishes its CPU legs
         dist.destroy_process_group()
 
 

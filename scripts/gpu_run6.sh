@@ -4,7 +4,7 @@ cd "$(dirname "$0")/.."
 O=gpurun_out/run6; mkdir -p $O
 nvidia-smi -L | tee $O/gpus.txt
 
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 > $O/bench_2gpu.json 2> $O/bench_2gpu.err
-tail -c 3000 $O/bench_2gpu.json; tail -5 $O/bench_2gpu.err
+(time timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 > $O/bench_2gpu.json 2> $O/bench_2gpu.err) 2>&1 | tail -3
+tail -c 3000 $O/bench_2gpu.json; grep "bench +" $O/bench_2gpu.err
 
 
