@@ -762,8 +762,6 @@ void launch_cross_attention_decode(const float* q, const __nv_bfloat16* k, const
             n_head, n_split == 1 ? 0 : evict_first);
 }
 
-void decode_ops_set_attributes() {}
-
 void launch_argmax_finalize(const DecodeState& st, const float* part_val, const int* part_idx, int n_tiles, int part_ld, int B,
                             int n_text_ctx, int eot, int honor_eot, int sot_len, cudaStream_t stream) {
   launch_pdl(argmax_finalize_kernel, dim3(B), dim3(128), 0, stream, st, part_val, part_idx, n_tiles, part_ld, n_text_ctx, eot, honor_eot, sot_len);

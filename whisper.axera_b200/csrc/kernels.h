@@ -15,9 +15,7 @@ void gemm_set_attributes();
 void logmel_set_attributes();
 void encoder_ops_set_attributes();
 void attention_tcgen05_set_attributes();
-void decode_ops_set_attributes();
 inline void kernels_set_attributes() {
-  decode_ops_set_attributes();
   gemm_set_attributes();
   logmel_set_attributes();
   encoder_ops_set_attributes();
