@@ -119,7 +119,7 @@ struct Conn {
     }
   }
   bool read_exact(std::string* out, size_t n) {
-    out->reserve(out->size() + n);
+    out->reserve(out->size() + std::min<size_t>(n, (size_t)16 << 20));  // a declared length is not trusted with memory up front
     while (n > 0) {
       if (pos == buf.size() && !fill()) return false;
       const size_t k = std::min(n, buf.size() - pos);
