@@ -726,14 +726,15 @@ void launch_self_attention_decode(const float* qkv, __nv_bfloat16* k_cache, __nv
 }
 
 int cross_attention_pick_split(int B, int n_head, int T) {
-  // 0 = streaming kernel (one resident wave, items claimed dynamically); n > 0 = cluster of n CTAs per item.  Few items:
-  // split every item over as many CTAs as it has segments so that enough loads are in flight; the arithmetic is the same.
+  // 0 = streaming kernel (one resident wave, items claimed dynamically); n > 0 = cluster of n CTAs per item: the smallest
+  // split that puts at least two CTAs on every SM (measured: 2 beats 3 and 6 at 128-384 items), the largest one when even
+  // that does not fill the machine (a handful of sequences).  The arithmetic is the same for every choice.
   static const int forced = getenv("B200W_CROSS_SPLIT") ? atoi(getenv("B200W_CROSS_SPLIT")) : -1;
   static const bool no_stream = getenv("B200W_NO_CROSS_STREAM") != nullptr;
   const int nseg = (T + kXKeysPerStep - 1) / kXKeysPerStep;
   const int n_items = B * n_head;
   if (T > kXMaxT) throw CudaError("cross attention: more keys than the kernels are sized for");
-  auto valid = [&](int n) { return n >= 1 && n <= 8 && nseg % n == 0 && nseg / n <= kXMaxSegPerCta && !(n == 1 && nseg > kXMaxSegPerCta); };
+  auto valid = [&](int n) { return n >= 1 && n <= 8 && nseg % n == 0 && nseg / n <= kXMaxSegPerCta; };  // portable cluster sizes only
   if (forced == 0) return 0;
   if (forced > 0 && valid(forced)) return forced;
   if (!no_stream && n_items >= 2 * kNumSMs) return 0;
