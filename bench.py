@@ -233,13 +233,19 @@ class Dist:
         if world > 1:
             import torch.distributed as dist
 
-            self.cpu_group = dist.new_group(backend="gloo")  # host-side waits that leave the GPUs idle (an NCCL barrier spins on them)
+            try:
+                self.cpu_group = dist.new_group(backend="gloo")  # host-side waits that leave the GPUs idle (an NCCL barrier spins on them)
+            except Exception as ex:  # no usable interface for gloo: fall back to the NCCL barrier
+                print("[bench] gloo group unavailable (%s): host waits use the NCCL barrier" % ex, file=sys.stderr, flush=True)
 
     def host_barrier(self):
         if self.world > 1:
             import torch.distributed as dist
 
-            dist.barrier(group=self.cpu_group)
+            if self.cpu_group is not None:
+                dist.barrier(group=self.cpu_group)
+            else:
+                dist.barrier()
 
     def barrier(self):
         import torch

@@ -22,6 +22,15 @@ dist.barrier()
 dist.all_reduce(t, op=dist.ReduceOp.MAX)
 gathered = [None] * world
 dist.all_gather_object(gathered, (lo, hi, local))
+# bench.py's host-side wait (a gloo sub-group: ranks whose GPUs are lent to rank 0's library handle wait without spinning on them)
+dd = bench.Dist(rank, 0, world)
+assert dd.cpu_group is not None
+dd.host_barrier()
+# strong split of configs[2]: 256 chunks over 1 / 2 / 4 / 8 ranks, long-form: 120 windows over 8
+for w in (1, 2, 4, 8):
+    parts = [bench.shard_range(256, r, w) for r in range(w)]
+    assert parts[0][0] == 0 and parts[-1][1] == 256 and all(a[1] == b[0] for a, b in zip(parts, parts[1:])) and all(h - l == 256 // w for l, h in parts)
+assert [h - l for l, h in (bench.shard_range(120, r, 8) for r in range(8))] == [15] * 8
 if rank == 0:
     assert abs(t.item() - 0.1 * world) < 1e-12
     covered = []
