@@ -37,3 +37,14 @@ def test_hf_checkpoint_round_trip(tmp_path):
         hf_logits = hf(input_features=torch.from_numpy(mel), decoder_input_ids=ids).logits
     for i in range(4):
         assert np.abs(hf_logits[:, 3 + i].numpy() - np.stack(r["logits"])[i]).max() <= 2e-4
+
+
+def test_known_model_name_does_not_override_the_checkpoint_shape(tmp_path):
+    """converting under one of the reference's model_type names (tiny / base / small / turbo) must still derive the
+    configuration from the tensors -- a deeper checkpoint saved as "turbo" would otherwise get turbo's 4-decoder-layer table."""
+    W = make_model.init_weights("micro")  # d = 128, 2 + 2 layers: not what the name "tiny" stands for
+    make_model.build_model_dir(str(tmp_path), "tiny", weights=W)
+    _, cfg = make_model.load_model_dir(str(tmp_path), "tiny")
+    a = make_model.ARCHS["micro"]
+    assert (cfg["n_text_state"], cfg["n_audio_layer"], cfg["n_text_layer"], cfg["n_text_head"]) == (a["d"], a["l_enc"], a["l_dec"], a["heads"])
+    assert cfg["n_text_state"] != make_model.ARCHS["tiny"]["d"]
